@@ -1,0 +1,332 @@
+"""CPU oracle for the estimate_transform path — numpy for the small linear algebra, C
+(oracle/pm_oracle.c via ctypes) for the O(N^2) loops.
+
+TEST INFRASTRUCTURE ONLY.  Imported by tests/, __graft_entry__.smoke() and the cpu_baseline /
+--impl reference legs of bench.py.  platymatch_b200/ never imports it.
+Parity is PINNED: tests/test_oracle_golden.py checks these functions against vectors dumped
+from the unmodified reference by oracle/make_golden.py (tests/golden/*.npz).
+
+Function names and signatures mirror the reference (paths relative to /root/reference):
+  platymatch/utils/utils.py:48-88, platymatch/estimate_transform/{shape_context,find_transform,
+  apply_transform,perform_icp}.py, and the pipeline body of platymatch/_dock_widget.py:526-721.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+NBINS = 360
+
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libpm_oracle.so")
+        if not os.path.exists(path):
+            build()
+        L = ctypes.CDLL(path)
+        L.pmo_mean_distance.restype = ctypes.c_double
+        L.pmo_mean_distance.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.pmo_shape_context_counts.restype = None
+        L.pmo_shape_context_counts.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                               ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                               ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.pmo_chi2_matrix.restype = None
+        L.pmo_chi2_matrix.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_void_p]
+        L.pmo_lsap.restype = ctypes.c_int
+        L.pmo_lsap.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                               ctypes.c_void_p, ctypes.c_void_p]
+        L.pmo_nearest.restype = None
+        L.pmo_nearest.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                  ctypes.c_void_p]
+        L.pmo_ransac_score.restype = None
+        L.pmo_ransac_score.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                       ctypes.c_int, ctypes.c_double, ctypes.c_void_p]
+        L.pmo_num_threads.restype = ctypes.c_int
+        L.pmo_set_num_threads.argtypes = [ctypes.c_int]
+        _LIB = L
+    return _LIB
+
+
+def num_threads():
+    return lib().pmo_num_threads()
+
+
+def set_num_threads(n):
+    lib().pmo_set_num_threads(int(n))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _n_by_3(detections, transposed):
+    """Reference convention (shape_context.py:151-157, utils.py:64-70): 3/4 x N unless transposed."""
+    d = np.asarray(detections, dtype=np.float64)
+    if not transposed:
+        d = d.transpose()
+    return np.ascontiguousarray(d[:, :3])
+
+
+# --------------------------------------------------------------------------- utils.py
+def get_centroid(detections, transposed=True):
+    """utils.py:48-56."""
+    d = np.asarray(detections, dtype=np.float64)
+    if transposed:
+        return np.mean(d[:, :3], 0, keepdims=True)
+    return np.mean(d[:3, :], 1, keepdims=True)
+
+
+def get_mean_distance(detections, transposed=True):
+    """utils.py:58-75 (mean over unordered pairs)."""
+    p = _n_by_3(detections, transposed)
+    return float(lib().pmo_mean_distance(_ptr(p), p.shape[0]))
+
+
+def get_error(moving_landmarks, fixed_landmarks):
+    """utils.py:77-88."""
+    if moving_landmarks is not None or fixed_landmarks is not None:
+        return float(np.mean(np.linalg.norm(moving_landmarks - fixed_landmarks, axis=0)))
+    return None
+
+
+# --------------------------------------------------------------------------- shape_context.py
+def r_edges(r_inner=1 / 8, r_outer=2, n_rbins=5):
+    """shape_context.py:24 — the exact doubles numpy produces (not exact powers of two)."""
+    return np.logspace(np.log10(r_inner), np.log10(r_outer), n_rbins)
+
+
+def pca_first_axis(points_n3):
+    """shape_context.py:162-165: sklearn PCA(n_components=3).fit(X).components_[0].
+
+    Restates scikit-learn's `covariance_eigh` full solver (chosen for n_samples >= 10 *
+    n_features, 3 features): C = (X^T X - n mu mu^T) / (n - 1); eigh; descending order;
+    svd_flip(u_based_decision=False): each component's largest-|.| entry made positive.
+    """
+    x = np.asarray(points_n3, dtype=np.float64)
+    n = x.shape[0]
+    mu = x.mean(axis=0)
+    c = x.T @ x
+    c -= n * np.outer(mu, mu)
+    c /= n - 1
+    w, v = np.linalg.eigh(c)
+    comp = v[:, ::-1].T  # rows = components, descending eigenvalue
+    axis = comp[0].copy()
+    if axis[np.argmax(np.abs(axis))] < 0:
+        axis = -axis
+    return axis
+
+
+VARIANT_SIGNS = {1: (1, 1), 2: (-1, -1), 3: (1, -1), 4: (-1, 1)}  # sc, sc2, sc3, sc4 (shape_context.py:170-185)
+
+
+def shape_context_counts(points_n3, centroid, mean_distance, x0, variant=1):
+    """Integer histogram (N,360) uint32 + dropped-neighbour count per nucleus, one orientation."""
+    p = np.ascontiguousarray(points_n3, dtype=np.float64)
+    n = p.shape[0]
+    c = np.ascontiguousarray(np.asarray(centroid, dtype=np.float64).reshape(-1)[:3])
+    x0 = np.ascontiguousarray(np.asarray(x0, dtype=np.float64).reshape(3))
+    e = np.ascontiguousarray(r_edges())
+    counts = np.zeros((n, NBINS), dtype=np.uint32)
+    dropped = np.zeros(n, dtype=np.uint32)
+    sx, sy = VARIANT_SIGNS[variant]
+    lib().pmo_shape_context_counts(_ptr(p), n, _ptr(c), _ptr(x0), float(mean_distance), sx, sy, _ptr(e), len(e),
+                                   _ptr(counts), _ptr(dropped))
+    return counts, dropped
+
+
+def normalise_counts(counts):
+    """shape_context.py:41: sc / sc.sum() on the float64 count vector."""
+    c = counts.astype(np.float64)
+    return c / c.sum(axis=1, keepdims=True)
+
+
+def get_unary(centroid, mean_distance, detections, type, transposed=False):
+    """shape_context.py:144-188: (sc, sc2, sc3, sc4), each (N,360) float64; sc3/sc4 empty for 'moving'."""
+    p = _n_by_3(detections, transposed)
+    x0 = pca_first_axis(p)
+    out = []
+    for variant in (1, 2, 3, 4):
+        if variant > 2 and type != "fixed":
+            out.append(np.array([]))
+            continue
+        counts, _ = shape_context_counts(p, centroid, mean_distance, x0, variant)
+        out.append(normalise_counts(counts))
+    return tuple(out)
+
+
+def get_unary_distance(sc1, sc2):
+    """shape_context.py:88-99 for one pair (scalar API)."""
+    a = np.ascontiguousarray(sc1, dtype=np.float64).reshape(1, -1)
+    b = np.ascontiguousarray(sc2, dtype=np.float64).reshape(1, -1)
+    return float(unary_distance_matrix(a, b)[0, 0])
+
+
+def unary_distance_matrix(sc_a, sc_b):
+    """The double loops of _dock_widget.py:556-602: U[i,j] = get_unary_distance(sc_a[i], sc_b[j])."""
+    a = np.ascontiguousarray(sc_a, dtype=np.float64)
+    b = np.ascontiguousarray(sc_b, dtype=np.float64)
+    out = np.empty((a.shape[0], b.shape[0]), dtype=np.float64)
+    lib().pmo_chi2_matrix(_ptr(a), a.shape[0], _ptr(b), b.shape[0], a.shape[1], _ptr(out))
+    return out
+
+
+# --------------------------------------------------------------------------- LAP
+def linear_sum_assignment(cost, return_stats=False):
+    """scipy.optimize.linear_sum_assignment (call sites _dock_widget.py:604-611): rows ascending,
+    min(nr, nc) pairs; wide matrices solved directly, tall ones through the transpose."""
+    c = np.asarray(cost, dtype=np.float64)
+    nr, nc = c.shape
+    transposed = nr > nc
+    if transposed:
+        c = c.T
+        nr, nc = nc, nr
+    c = np.ascontiguousarray(c)
+    col4row = np.empty(nr, dtype=np.int64)
+    u = np.empty(nr)
+    v = np.empty(nc)
+    steps = ctypes.c_int64(0)
+    rc = lib().pmo_lsap(_ptr(c), nr, nc, _ptr(col4row), _ptr(u), _ptr(v), ctypes.byref(steps))
+    if rc != 0:
+        raise ValueError("cost matrix is infeasible")
+    rows = np.arange(nr, dtype=np.int64)
+    if transposed:
+        order = np.argsort(col4row)
+        rows, col4row = col4row[order], rows[order]
+    if return_stats:
+        return rows, col4row, dict(u=u, v=v, steps=steps.value)
+    return rows, col4row
+
+
+# --------------------------------------------------------------------------- find_transform.py / apply_transform.py
+def get_affine_transform(moving, fixed, with_ones=False):
+    """find_transform.py:4-17: fixed_h @ pinv(moving_h)."""
+    moving = np.asarray(moving, dtype=np.float64)
+    fixed = np.asarray(fixed, dtype=np.float64)
+    if not with_ones:
+        ones = np.ones((1, moving.shape[1]))
+        moving = np.vstack((moving, ones))
+        fixed = np.vstack((fixed, ones))
+    return np.matmul(fixed, np.linalg.pinv(moving))
+
+
+def apply_affine_transform(moving, affine_transform_matrix):
+    """apply_transform.py:3-17."""
+    moving = np.asarray(moving, dtype=np.float64)[:3, :]
+    moving = np.vstack((moving, np.ones((1, moving.shape[1]))))
+    return np.matmul(affine_transform_matrix, moving)[:3, :]
+
+
+# --------------------------------------------------------------------------- RANSAC
+def ransac_sample_indices(k, min_samples, trials, seed):
+    """The index stream do_ransac draws (shape_context.py:122) when the global numpy RNG was
+    seeded with `seed`: RandomState(seed).choice(k, min_samples, replace=False) per trial."""
+    rs = np.random.RandomState(seed)
+    return np.stack([rs.choice(k, min_samples, replace=False) for _ in range(trials)]).astype(np.int32)
+
+
+def do_ransac(moving_all, fixed_all, min_samples=4, trials=500, error=5, transform="Affine", sample_indices=None,
+              seed=None, return_all=False):
+    """shape_context.py:103-139 with the sample-index stream made explicit (first strictly-better wins)."""
+    assert transform == "Affine"
+    moving_all = np.asarray(moving_all, dtype=np.float64)[:3, :]
+    fixed_all = np.asarray(fixed_all, dtype=np.float64)[:3, :]
+    k = fixed_all.shape[1]
+    if sample_indices is None:
+        sample_indices = ransac_sample_indices(k, min_samples, trials, seed)
+    trials = sample_indices.shape[0]
+    mats = np.empty((trials, 4, 4))
+    for t in range(trials):
+        idx = sample_indices[t]
+        mats[t] = get_affine_transform(moving_all[:, idx], fixed_all[:, idx])
+    m = np.ascontiguousarray(moving_all.T)
+    f = np.ascontiguousarray(fixed_all.T)
+    inl = np.zeros(trials, dtype=np.int32)
+    lib().pmo_ransac_score(_ptr(m), _ptr(f), k, _ptr(np.ascontiguousarray(mats)), trials, float(error), _ptr(inl))
+    a_best, inliers_best = np.ones((4, 4)), 0
+    if trials and inl.max() > 0:
+        t = int(np.argmax(inl))  # first maximum == first strictly-better
+        a_best, inliers_best = mats[t], int(inl[t])
+    if return_all:
+        return a_best, inliers_best, inl, mats
+    return a_best, inliers_best
+
+
+# --------------------------------------------------------------------------- ICP
+def nearest(moving, fixed):
+    """perform_icp.py:15-16 for 3xN inputs: index of the nearest fixed point per moving point."""
+    m = np.ascontiguousarray(np.asarray(moving, dtype=np.float64)[:3].T)
+    f = np.ascontiguousarray(np.asarray(fixed, dtype=np.float64)[:3].T)
+    nn = np.empty(m.shape[0], dtype=np.int64)
+    dist = np.empty(m.shape[0])
+    lib().pmo_nearest(_ptr(m), m.shape[0], _ptr(f), f.shape[0], _ptr(nn), _ptr(dist))
+    return nn, dist
+
+
+def perform_icp(moving, fixed, icp_iterations=50, transform="Affine", return_residuals=False):
+    """perform_icp.py:7-26."""
+    assert transform == "Affine"
+    moving = np.asarray(moving, dtype=np.float64)[:3, :]
+    fixed = np.asarray(fixed, dtype=np.float64)[:3, :]
+    a_icp = np.identity(4)
+    residuals = []
+    for _ in range(icp_iterations):
+        i2, _d = nearest(moving, fixed)
+        a_est = get_affine_transform(moving, fixed[:, i2])
+        moving = apply_affine_transform(moving, a_est)
+        residuals.append(get_error(moving, fixed[:, i2]))
+        a_icp = np.matmul(a_est, a_icp)
+    if return_residuals:
+        return a_icp, np.array(residuals)
+    return a_icp
+
+
+# --------------------------------------------------------------------------- pipeline (_dock_widget.py:526-721)
+HYPOTHESES = [(1, 1), (1, 2), (1, 3), (1, 4), (2, 1), (2, 2), (2, 3), (2, 4)]  # U11..U14, U21..U24
+
+
+def estimate_transform_unsupervised(moving, fixed, ransac_samples=4, ransac_trials=8000, ransac_error=16,
+                                    icp_iterations=50, seed=0, hypotheses=None, sample_indices=None):
+    moving = np.asarray(moving, dtype=np.float64)
+    fixed = np.asarray(fixed, dtype=np.float64)
+    mc, fc = get_centroid(moving, False), get_centroid(fixed, False)
+    md, fd = get_mean_distance(moving, False), get_mean_distance(fixed, False)
+    um = get_unary(mc, md, moving, "moving")
+    uf = get_unary(fc, fd, fixed, "fixed")
+    hyps = HYPOTHESES if hypotheses is None else hypotheses
+    res = dict(inliers=[], ransac_A=[], assignments=[], lap_cost=[])
+    rs = np.random.RandomState(seed)
+    for q, (a, b) in enumerate(hyps):
+        U = unary_distance_matrix(um[a - 1], uf[b - 1])
+        r, c = linear_sum_assignment(U)
+        if sample_indices is not None:
+            idx = sample_indices[q]
+        else:
+            idx = np.stack([rs.choice(len(r), ransac_samples, replace=False) for _ in range(ransac_trials)])
+        A, inl = do_ransac(moving[:, r], fixed[:, c], ransac_samples, ransac_trials, ransac_error, sample_indices=idx)
+        res["inliers"].append(inl)
+        res["ransac_A"].append(A)
+        res["assignments"].append((r, c))
+        res["lap_cost"].append(float(U[r, c].sum()))
+    best = int(np.argmax(res["inliers"]))
+    a_sc = res["ransac_A"][best]
+    a_icp, resid = perform_icp(apply_affine_transform(moving, a_sc), fixed, icp_iterations, return_residuals=True)
+    res.update(best=best, transform_sc=a_sc, transform_icp=a_icp, transform=a_icp @ a_sc, icp_residuals=resid)
+    return res
+
+
+def estimate_transform_supervised(moving, fixed, moving_keypoints, fixed_keypoints, icp_iterations=50):
+    """_dock_widget.py:707-717: LS affine on the keypoints, then ICP."""
+    a_sc = get_affine_transform(moving_keypoints, fixed_keypoints)
+    a_icp, resid = perform_icp(apply_affine_transform(moving, a_sc), fixed, icp_iterations, return_residuals=True)
+    return dict(transform_sc=a_sc, transform_icp=a_icp, transform=a_icp @ a_sc, icp_residuals=resid)

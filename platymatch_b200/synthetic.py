@@ -1,0 +1,71 @@
+"""Synthetic embryo-like nuclei clouds (BASELINE.json `configs`).
+
+Host-side numpy only: this is the workload generator used by tests and bench.py, not part of
+the registration path.  Clouds are modelled on the reference's test assets
+(`platymatch/_tests/assets/02-insitu.csv`: 331 nuclei on a thick near-spherical shell, radius
+~122 px, nearest-neighbour spacing ~19 px, zyx pixel coordinates).
+"""
+import numpy as np
+
+__all__ = ["make_fixed_cloud", "random_affine", "make_pair", "make_keypoints", "make_specimens"]
+
+
+def make_fixed_cloud(n, rng):
+    """(3, n) float64 zyx cloud: shell of radius 122*sqrt(n/331) +- 8 px, axes (1.10, 1.00, 0.92)."""
+    s = np.sqrt(n / 331.0)
+    d = rng.standard_normal((3, n))
+    d /= np.linalg.norm(d, axis=0, keepdims=True)
+    r = 122.0 * s + rng.normal(0.0, 8.0, size=n)
+    pts = d * r * np.array([[1.10], [1.00], [0.92]])
+    return pts + np.array([[350.0], [270.0], [280.0]]) * s
+
+
+def random_affine(rng):
+    """4x4: (QR-orthogonal x diag U(0.9,1.1)) linear part, translation U(-100,100)^3."""
+    q, r = np.linalg.qr(rng.standard_normal((3, 3)))
+    q = q * np.sign(np.diag(r))  # unique QR
+    a = np.eye(4)
+    a[:3, :3] = q @ np.diag(rng.uniform(0.9, 1.1, size=3))
+    a[:3, 3] = rng.uniform(-100.0, 100.0, size=3)
+    return a
+
+
+def make_pair(n_fixed, seed=None, jitter=2.0, dropout=0.10):
+    """One registration problem.
+
+    Returns dict(moving (3,N1), fixed (3,N2), A_gt (4,4) with fixed ~= A_gt @ moving,
+    gt_fixed_index (N1,) = index into fixed of each moving nucleus' true partner).
+    """
+    rng = np.random.default_rng(n_fixed if seed is None else seed)
+    fixed = make_fixed_cloud(n_fixed, rng)
+    a_gt = random_affine(rng)
+    a_inv = np.linalg.inv(a_gt)
+    moving_all = a_inv[:3, :3] @ fixed + a_inv[:3, 3:4]
+    moving_all = moving_all + rng.normal(0.0, jitter, size=moving_all.shape)
+    keep = rng.permutation(n_fixed)[: n_fixed - int(round(dropout * n_fixed))]
+    keep = rng.permutation(keep)
+    return {"moving": np.ascontiguousarray(moving_all[:, keep]), "fixed": fixed, "A_gt": a_gt,
+            "gt_fixed_index": keep.astype(np.int64)}
+
+
+def make_keypoints(pair, n_keypoints=10, seed=0, jitter=1.0):
+    """Keypoint-supervised config: n ground-truth pairs among surviving nuclei (+ click jitter)."""
+    rng = np.random.default_rng(seed)
+    sel = rng.choice(pair["moving"].shape[1], n_keypoints, replace=False)
+    mk = pair["moving"][:, sel] + rng.normal(0.0, jitter, size=(3, n_keypoints))
+    fk = pair["fixed"][:, pair["gt_fixed_index"][sel]] + rng.normal(0.0, jitter, size=(3, n_keypoints))
+    return mk, fk
+
+
+def make_specimens(n_specimens=12, n_nuclei=8000, jitter=2.0, dropout=0.10, seed=0):
+    """Batched all-pairs config: specimens are random-affine, jittered, thinned views of one atlas."""
+    rng = np.random.default_rng(seed)
+    atlas = make_fixed_cloud(int(round(n_nuclei / (1.0 - dropout))), rng)
+    out = []
+    for s in range(n_specimens):
+        r = np.random.default_rng(1000 + s)
+        a = random_affine(r)
+        pts = a[:3, :3] @ atlas + a[:3, 3:4] + r.normal(0.0, jitter, size=atlas.shape)
+        keep = r.permutation(atlas.shape[1])[:n_nuclei]
+        out.append({"points": np.ascontiguousarray(pts[:, keep]), "A": a, "atlas_index": keep})
+    return out
