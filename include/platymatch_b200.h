@@ -1,0 +1,173 @@
+/*
+ * platymatch_b200.h — C ABI of libplatymatch_b200.so (hand-written CUDA for sm_100a).
+ *
+ * Drop-in boundary for the estimate_transform hot path of juglab/PlatyMatch.  The reference has no
+ * FFI layer: its boundary is the Python function API imported by the napari widget
+ * (platymatch/_dock_widget.py:10,16-21).  Every entry point below names the reference function
+ * (file:line, relative to the reference repo) whose arithmetic it replaces; INTEGRATION.md shows
+ * the ctypes stub a maintainer would put behind each reference function.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / numpy types.
+ *   - `pm_*` entry points take DEVICE pointers and a `cudaStream_t` passed as `void*` (0 = legacy
+ *     default stream); they enqueue work and return without synchronising unless stated.
+ *     The caller owns every buffer (inputs, outputs, workspace); the library never frees or
+ *     retains a pointer after the call's work has completed on the stream.
+ *   - `pm_host_*` entry points take HOST pointers (what a numpy caller holds), copy in, run,
+ *     copy out and synchronise.
+ *   - point clouds are N x 3 float64 row-major, coordinate order as given (the reference uses zyx);
+ *     transforms are 4 x 4 float64 row-major acting on column vectors (apply_transform.py:14-17).
+ *   - return value: 0 = ok; negative = error (PM_ERR_*), message via pm_last_error_string().
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef PLATYMATCH_B200_H
+#define PLATYMATCH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM_OK 0
+#define PM_ERR_INVALID_ARGUMENT (-1)
+#define PM_ERR_CUDA (-2)
+#define PM_ERR_WORKSPACE (-3)
+#define PM_ERR_INFEASIBLE (-4)
+#define PM_ERR_UNSUPPORTED (-5)
+
+#define PM_NBINS 360          /* 5 r x 6 theta x 12 phi  (shape_context.py:10) */
+#define PM_STATS_DOUBLES 16   /* layout of the cloud-stats block, see pm_cloud_stats */
+
+/* ---- library ------------------------------------------------------------------------------ */
+int pm_version(void);
+const char *pm_last_error_string(void);  /* thread-local; valid until the next failing call */
+int pm_device_count(void);               /* number of visible CUDA devices (0 if none) */
+int pm_sm_count(int device);
+/* number of kernels this library has launched in this process (bench.py's `gpu_launches`) */
+unsigned long long pm_launch_count(void);
+/* FP32 FMA issue-rate probe: `blocks` x 256 threads, each `iters` x 16 dependent-chain-free FFMAs;
+ * returns the FLOP count through *flops_out (host); time it with events around the call. */
+int pm_probe_fp32_fma(int blocks, int iters, float *sink, double *flops_out, void *stream);
+
+/* ---- K0  cloud statistics -------------------------------------------------------------------
+ * get_centroid (platymatch/utils/utils.py:48-56) and the PCA first axis computed inside get_unary
+ * (shape_context.py:162-165: sklearn PCA.components_[0], sign: largest-|.| entry positive).
+ * stats[0:3] centroid, stats[3:6] first principal axis x0, stats[6:12] covariance (xx,xy,xz,yy,yz,zz,
+ * divided by n-1), stats[12] n, stats[13:16] eigenvalues descending.  All float64 on device. */
+int pm_cloud_stats(const double *pts, int n, double *stats, void *stream);
+
+/* ---- K1  mean pairwise distance -------------------------------------------------------------
+ * get_mean_distance (utils.py:58-75): mean of ||p_i - p_j|| over unordered pairs.  Deterministic
+ * (fixed-order two-level reduction).  out_mean: 1 float64 on device.
+ * workspace: pm_mean_distance_workspace_bytes(n) bytes on device. */
+size_t pm_mean_distance_workspace_bytes(int n);
+int pm_mean_distance(const double *pts, int n, double *out_mean, void *workspace, size_t workspace_bytes,
+                     void *stream);
+
+/* ---- K2  3D log-polar shape-context histograms ------------------------------------------------
+ * get_unary / transform / get_shape_context / get_bin_index (shape_context.py:144-188, :61-84,
+ * :10-42, :46-58).  For every nucleus builds the local frame (z radial from `centroid`, x = x0
+ * Gram-Schmidt'ed against z, y = z x x) and bins all other nuclei: r/mean_dist against r_edges
+ * (ring n_redges-1 open-ended), theta = acos(c/r) // (pi/6), phi = atan2 wrapped // (pi/6), linear
+ * index un-clamped, indices outside 0..359 and NaN dropped — float64 throughout, numpy `//` semantics.
+ * n_variants = 2 ('moving': sc, sc2) or 4 ('fixed': sc, sc2, sc3, sc4) or 1 (sc only).
+ *   centroid   3 float64 (device)     x0  3 float64 (device)    mean_dist 1 float64 (device)
+ *   r_edges    n_redges float64 (device) — numpy's logspace(log10(1/8), log10(2), 5) doubles
+ *   counts     [n_variants][n][360] uint32  integer histograms (reference row = counts / row sum)
+ *   dropped    [n_variants][n] uint32       neighbours not counted (overflow bins / NaN)
+ *   edge_ties  [1] uint64, accumulated: neighbours whose r, theta or phi lies within 64 ulp of a
+ *              bin edge (where another libm could decide differently); may be NULL. */
+int pm_shape_context_hist(const double *pts, int n, const double *centroid, const double *x0,
+                          const double *mean_dist, const double *r_edges, int n_redges, int n_variants,
+                          uint32_t *counts, uint32_t *dropped, unsigned long long *edge_ties, void *stream);
+
+/* Normalise integer histograms (shape_context.py:41) to float32 for the cost kernel, written
+ * bin-major ("transposed"): out[k * ld + i] = counts[i][k] / rowsum_i, ld >= n (pad columns are
+ * zero-filled up to ld).  zero_sentinel replaces exact zeros (0 keeps them; the chi2 kernel wants
+ * its B operand with PM_CHI2_ZERO_SENTINEL so that 0/0 bins contribute 0 without a branch). */
+#define PM_CHI2_ZERO_SENTINEL 1e-30f
+int pm_normalise_hist(const uint32_t *counts, int n, float *out, int ld, float zero_sentinel, void *stream);
+
+/* ---- K3  chi^2 histogram-distance cost matrix ---------------------------------------------------
+ * get_unary_distance (shape_context.py:88-99) over all pairs (_dock_widget.py:547-602):
+ * cost[i][j] = 0.5 * sum_k (a_ik - b_jk)^2 / (a_ik + b_jk), equal bins skipped.  FP32, register tiled.
+ *   a_t  [360][lda] float32 bin-major histograms of the ROW cloud (exact zeros)
+ *   b_t  [360][ldb] float32 bin-major histograms of the COLUMN cloud (zeros = PM_CHI2_ZERO_SENTINEL)
+ *   rows [row_begin,row_end) of the n1 x n2 matrix are written to cost + (i - row_begin) * ldc
+ * (row sharding across GPUs: each rank passes its own range and buffer). */
+int pm_chi2_cost(const float *a_t, int lda, int n1, const float *b_t, int ldb, int n2, int row_begin,
+                 int row_end, float *cost, int ldc, void *stream);
+
+/* ---- K4  linear sum assignment ------------------------------------------------------------------
+ * Replaces scipy.optimize.linear_sum_assignment at _dock_widget.py:604-611 for nr <= nc
+ * (the host mirror transposes otherwise, as scipy does).  Exact: dual-feasible parallel bidding
+ * (epsilon = 0, keeps complementary slackness exactly) followed by shortest augmenting paths with
+ * float64 duals — optimal for the float32 matrix given.
+ *   cost     [batch][nr][ldc] float32, ldc >= nc
+ *   col4row  [batch][nr] int32 out (column assigned to each row; rows are implicitly 0..nr-1)
+ *   total    [batch] float64 out: sum of assigned costs
+ *   stats    [batch][PM_LAP_STATS] int64 out, may be NULL (see PM_LAP_STAT_*)
+ * workspace: pm_lap_workspace_bytes(batch, nr, nc). */
+#define PM_LAP_STATS 8
+#define PM_LAP_STAT_BID_ROUNDS 0
+#define PM_LAP_STAT_ROWS_AFTER_BIDDING 1
+#define PM_LAP_STAT_AUGMENTATIONS 2
+#define PM_LAP_STAT_DIJKSTRA_STEPS 3
+#define PM_LAP_STAT_STATUS 4 /* 0 ok, -4 infeasible */
+size_t pm_lap_workspace_bytes(int batch, int nr, int nc);
+int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ldc, int max_bid_rounds, int32_t *col4row,
+                 double *total, int64_t *stats, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- K5  affine RANSAC ---------------------------------------------------------------------------
+ * do_ransac (shape_context.py:103-139) with get_affine_transform (find_transform.py:4-17) on the
+ * sampled pairs and apply_affine_transform (apply_transform.py:3-17) + inlier count on all pairs.
+ *   moving, fixed   [k][3] float64, already in correspondence order (_dock_widget.py:622-623)
+ *   sample_idx      [trials][min_samples] int32 (device) or NULL -> drawn on device from `seed`
+ *                   (Philox counter RNG, distinct indices per trial)
+ *   best_A [16] float64, best_inliers [1] int32, best_trial [1] int32  (first strictly-better trial;
+ *   A = all ones and inliers = 0 if no trial has an inlier, as the reference)
+ *   inliers_per_trial  [trials] int32 out, may be NULL.
+ * workspace: pm_ransac_workspace_bytes(trials). */
+size_t pm_ransac_workspace_bytes(int trials);
+int pm_ransac_affine(const double *moving, const double *fixed, int k, const int32_t *sample_idx, int trials,
+                     int min_samples, double error, unsigned long long seed, double *best_A,
+                     int32_t *best_inliers, int32_t *best_trial, int32_t *inliers_per_trial, void *workspace,
+                     size_t workspace_bytes, void *stream);
+
+/* ---- K6  ICP with affine re-fit -------------------------------------------------------------------
+ * perform_icp (perform_icp.py:7-26): `iterations` x { nearest fixed point per moving point (first
+ * minimum wins), least-squares affine over all pairs (find_transform.py:4-17 = F M^T (M M^T)^-1),
+ * apply, compose }.  Always exactly `iterations` iterations.
+ *   moving [n1][3] float64 — NOT modified;  fixed [n2][3] float64
+ *   A_icp [16] float64 out; residuals [iterations] float64 out (mean ||moving' - fixed[nn]||,
+ *   get_error utils.py:77-88), may be NULL;  nn_out [n1] int32 last nearest-neighbour map, may be NULL.
+ * workspace: pm_icp_workspace_bytes(n1). */
+size_t pm_icp_workspace_bytes(int n1);
+int pm_icp_affine(const double *moving, int n1, const double *fixed, int n2, int iterations, double *A_icp,
+                  double *residuals, int32_t *nn_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- small ops -------------------------------------------------------------------------------------
+ * get_affine_transform (find_transform.py:4-17) for K >= 4 pairs, normal equations in float64. */
+int pm_fit_affine(const double *moving, const double *fixed, int k, double *A, void *stream);
+/* apply_affine_transform (apply_transform.py:3-17): out[i] = (A [p_i;1])[:3];  in-place allowed. */
+int pm_apply_affine(const double *pts, int n, const double *A, double *out, void *stream);
+/* out[i] = pts[index[i]] (the reordering moving[:, row_ind] / fixed[:, col_ind], _dock_widget.py:622-623) */
+int pm_gather_points(const double *pts, const int32_t *index, int k, double *out, void *stream);
+/* C = A @ B for 4x4 float64 (icp @ sc, _dock_widget.py:428) */
+int pm_compose(const double *A, const double *B, double *C, void *stream);
+
+/* ---- host-buffer entry points (numpy callers; copy in, run, copy out, synchronise) ----------------- */
+/* get_mean_distance (utils.py:58-75) */
+int pm_host_mean_distance(const double *pts, int n, int device, double *out_mean);
+/* get_unary (shape_context.py:144-188): counts [n_variants][n][360] uint32, dropped [n_variants][n],
+ * x0_out[3] (PCA axis used), edge_ties_out (may be NULL). */
+int pm_host_shape_context(const double *pts, int n, const double *centroid, double mean_dist,
+                          const double *r_edges, int n_redges, int n_variants, int device, uint32_t *counts,
+                          uint32_t *dropped, double *x0_out, unsigned long long *edge_ties_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLATYMATCH_B200_H */

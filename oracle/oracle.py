@@ -40,6 +40,11 @@ def lib():
         L.pmo_shape_context_counts.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                                ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                                ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.pmo_shape_context_counts_range.restype = None
+        L.pmo_shape_context_counts_range.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                                     ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                     ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                     ctypes.c_void_p]
         L.pmo_chi2_matrix.restype = None
         L.pmo_chi2_matrix.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_void_p]
@@ -130,10 +135,22 @@ def pca_first_axis(points_n3):
 VARIANT_SIGNS = {1: (1, 1), 2: (-1, -1), 3: (1, -1), 4: (-1, 1)}  # sc, sc2, sc3, sc4 (shape_context.py:170-185)
 
 
-def shape_context_counts(points_n3, centroid, mean_distance, x0, variant=1):
-    """Integer histogram (N,360) uint32 + dropped-neighbour count per nucleus, one orientation."""
+def shape_context_counts(points_n3, centroid, mean_distance, x0, variant=1, query_range=None):
+    """Integer histogram (N,360) uint32 + dropped-neighbour count per nucleus, one orientation.
+    query_range=(i0, i1) restricts the query nuclei (rows) for bounded-sample timings."""
     p = np.ascontiguousarray(points_n3, dtype=np.float64)
     n = p.shape[0]
+    if query_range is not None:
+        i0, i1 = query_range
+        c = np.ascontiguousarray(np.asarray(centroid, dtype=np.float64).reshape(-1)[:3])
+        x0 = np.ascontiguousarray(np.asarray(x0, dtype=np.float64).reshape(3))
+        e = np.ascontiguousarray(r_edges())
+        counts = np.zeros((i1 - i0, NBINS), dtype=np.uint32)
+        dropped = np.zeros(i1 - i0, dtype=np.uint32)
+        sx, sy = VARIANT_SIGNS[variant]
+        lib().pmo_shape_context_counts_range(_ptr(p), n, _ptr(c), _ptr(x0), float(mean_distance), sx, sy, _ptr(e),
+                                             len(e), i0, i1, _ptr(counts), _ptr(dropped))
+        return counts, dropped
     c = np.ascontiguousarray(np.asarray(centroid, dtype=np.float64).reshape(-1)[:3])
     x0 = np.ascontiguousarray(np.asarray(x0, dtype=np.float64).reshape(3))
     e = np.ascontiguousarray(r_edges())

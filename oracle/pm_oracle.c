@@ -112,11 +112,24 @@ static int pmo_bin_of(double a, double b, double c, double mean_dist, const doub
  *   dropped   N: neighbours that landed outside bins 0..359 or were NaN
  * Local coordinates are the dot products of (q - p) with the frame, which is what
  * transform() (:61-84, T = B inv(A)) evaluates for an orthonormal frame. */
+void pmo_shape_context_counts_range(const double *pts, int n, const double *centroid, const double *x0,
+                                    double mean_dist, int sign_x, int sign_y, const double *r_edges,
+                                    int n_redges, int i_begin, int i_end, uint32_t *counts, uint32_t *dropped);
+
 void pmo_shape_context_counts(const double *pts, int n, const double *centroid, const double *x0,
                               double mean_dist, int sign_x, int sign_y, const double *r_edges,
                               int n_redges, uint32_t *counts, uint32_t *dropped) {
+    pmo_shape_context_counts_range(pts, n, centroid, x0, mean_dist, sign_x, sign_y, r_edges, n_redges, 0, n,
+                                   counts, dropped);
+}
+
+/* Same, for query nuclei [i_begin, i_end) only (all n nuclei are still the neighbours); row i is
+ * written at counts + (i - i_begin) * 360.  Used for bounded-sample CPU timings. */
+void pmo_shape_context_counts_range(const double *pts, int n, const double *centroid, const double *x0,
+                                    double mean_dist, int sign_x, int sign_y, const double *r_edges,
+                                    int n_redges, int i_begin, int i_end, uint32_t *counts, uint32_t *dropped) {
 #pragma omp parallel for schedule(dynamic, 8)
-    for (int i = 0; i < n; ++i) {
+    for (int i = i_begin; i < i_end; ++i) {
         const double *p = pts + 3 * i;
         double z[3], x[3], y[3];
         double dz[3] = {p[0] - centroid[0], p[1] - centroid[1], p[2] - centroid[2]};
@@ -135,7 +148,7 @@ void pmo_shape_context_counts(const double *pts, int n, const double *centroid, 
          * negate that y (:180-181), so the effective sign on cross(z, x) is sign_x * sign_y. */
         double sy = (double)(sign_x * sign_y);
         for (int k = 0; k < 3; ++k) y[k] = sy * (y[k] / ny);
-        uint32_t *h = counts + (size_t)i * PMO_NBINS;
+        uint32_t *h = counts + (size_t)(i - i_begin) * PMO_NBINS;
         memset(h, 0, PMO_NBINS * sizeof(uint32_t));
         uint32_t drop = 0;
         for (int j = 0; j < n; ++j) {
@@ -148,7 +161,7 @@ void pmo_shape_context_counts(const double *pts, int n, const double *centroid, 
             int bin = pmo_bin_of(a, b, c, mean_dist, r_edges, n_redges);
             if (bin < 0) ++drop; else ++h[bin];
         }
-        if (dropped) dropped[i] = drop;
+        if (dropped) dropped[i - i_begin] = drop;
     }
 }
 

@@ -1,0 +1,171 @@
+"""Device-resident building blocks: thin Python over the C ABI, torch tensors as device buffers.
+
+Every function here takes / returns CUDA tensors and enqueues on the current torch stream; nothing
+synchronises unless stated.  The reference-named numpy API (utils/, estimate_transform/) and the
+fused pipeline (pipeline.py) are built from these.
+"""
+import numpy as np
+
+from . import _lib
+from ._lib import NBINS, LAP_STATS, CHI2_TILE, check, ptr, stream_ptr, load
+
+R_EDGES = np.logspace(np.log10(1 / 8), np.log10(2), 5)  # shape_context.py:24 — numpy's exact doubles
+
+
+def _torch():
+    return _lib.require_cuda()
+
+
+def to_device_points(cloud, transposed=False, device=None):
+    """numpy 3xN / 4xN (reference layout) or Nx3/4 (transposed=True) -> CUDA [N,3] float64."""
+    torch = _torch()
+    if torch.is_tensor(cloud):
+        t = cloud.to(dtype=torch.float64)
+        t = t if transposed else t.t()
+        return t[:, :3].contiguous().to(device or "cuda")
+    a = np.asarray(cloud, dtype=np.float64)
+    a = a if transposed else a.T
+    a = np.ascontiguousarray(a[:, :3])
+    return torch.from_numpy(a).to(device or "cuda", non_blocking=True)
+
+
+def cloud_stats(pts):
+    """[16] float64: centroid[0:3], PCA first axis[3:6], covariance[6:12], n, eigenvalues[13:16]."""
+    torch = _torch()
+    stats = torch.empty(16, dtype=torch.float64, device=pts.device)
+    check(load().pm_cloud_stats(ptr(pts), pts.shape[0], ptr(stats), stream_ptr()), "pm_cloud_stats")
+    return stats
+
+
+def mean_distance(pts):
+    """[1] float64 device scalar (utils.py:58-75)."""
+    torch = _torch()
+    n = pts.shape[0]
+    nbytes = load().pm_mean_distance_workspace_bytes(n)
+    ws = torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=pts.device)
+    out = torch.empty(1, dtype=torch.float64, device=pts.device)
+    check(load().pm_mean_distance(ptr(pts), n, ptr(out), ptr(ws), nbytes, stream_ptr()), "pm_mean_distance")
+    return out
+
+
+def shape_context_counts(pts, centroid, x0, mean_dist, n_variants, r_edges=None):
+    """Integer histograms [n_variants, N, 360] uint32 (as int32 tensor), dropped [n_variants, N], ties [1]."""
+    torch = _torch()
+    n = pts.shape[0]
+    if r_edges is None:
+        r_edges = torch.from_numpy(R_EDGES).to(pts.device)
+    counts = torch.empty((n_variants, n, NBINS), dtype=torch.int32, device=pts.device)
+    dropped = torch.empty((n_variants, n), dtype=torch.int32, device=pts.device)
+    ties = torch.zeros(1, dtype=torch.int64, device=pts.device)
+    check(load().pm_shape_context_hist(ptr(pts), n, ptr(centroid), ptr(x0), ptr(mean_dist), ptr(r_edges),
+                                       r_edges.numel(), n_variants, ptr(counts), ptr(dropped), ptr(ties),
+                                       stream_ptr()), "pm_shape_context_hist")
+    return counts, dropped, ties
+
+
+def padded(n, tile=CHI2_TILE):
+    return ((n + tile - 1) // tile) * tile
+
+
+def normalise(counts_2d, zero_sentinel=0.0):
+    """[N,360] counts -> bin-major float32 [360, ld] (ld = N rounded up to the chi2 tile)."""
+    torch = _torch()
+    n = counts_2d.shape[0]
+    ld = padded(n)
+    out = torch.empty((NBINS, ld), dtype=torch.float32, device=counts_2d.device)
+    check(load().pm_normalise_hist(ptr(counts_2d), n, ptr(out), ld, float(zero_sentinel), stream_ptr()),
+          "pm_normalise_hist")
+    return out
+
+
+def chi2_cost(a_t, n1, b_t, n2, out=None, row_begin=0, row_end=None):
+    """cost[row_begin:row_end, :n2] float32 (ld = n2 rounded up to 4); a_t exact zeros, b_t sentinel zeros."""
+    torch = _torch()
+    row_end = n1 if row_end is None else row_end
+    ldc = (n2 + 3) // 4 * 4
+    if out is None:
+        out = torch.empty((row_end - row_begin, ldc), dtype=torch.float32, device=a_t.device)
+    assert out.stride(-1) == 1 and out.shape[-1] >= n2
+    check(load().pm_chi2_cost(ptr(a_t), a_t.shape[1], n1, ptr(b_t), b_t.shape[1], n2, row_begin, row_end, ptr(out),
+                              out.stride(-2), stream_ptr()), "pm_chi2_cost")
+    return out
+
+
+def lap_solve(cost, nr, nc, max_bid_rounds=128):
+    """cost [batch, nr, ldc] float32 (nr <= nc) -> col4row [batch, nr] int32, total [batch] f64, stats [batch, 8] i64."""
+    torch = _torch()
+    if cost.dim() == 2:
+        cost = cost.unsqueeze(0)
+    batch, ldc = cost.shape[0], cost.stride(1)
+    assert cost.stride(2) == 1 and cost.stride(0) == nr * ldc, "cost batch must be densely stacked"
+    col4row = torch.empty((batch, nr), dtype=torch.int32, device=cost.device)
+    total = torch.empty(batch, dtype=torch.float64, device=cost.device)
+    stats = torch.zeros((batch, LAP_STATS), dtype=torch.int64, device=cost.device)
+    nbytes = load().pm_lap_workspace_bytes(batch, nr, nc)
+    ws = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=cost.device)
+    check(load().pm_lap_solve(ptr(cost), batch, nr, nc, ldc, int(max_bid_rounds), ptr(col4row), ptr(total), ptr(stats),
+                              ptr(ws), nbytes, stream_ptr()), "pm_lap_solve")
+    return col4row, total, stats
+
+
+def ransac_affine(moving_k, fixed_k, trials, error, min_samples=4, sample_idx=None, seed=0, want_per_trial=False):
+    """moving_k / fixed_k [K,3] in correspondence order -> (A [16], inliers [1] i32, trial [1] i32, per_trial|None)."""
+    torch = _torch()
+    k = moving_k.shape[0]
+    dev = moving_k.device
+    best_a = torch.empty(16, dtype=torch.float64, device=dev)
+    best_inl = torch.empty(1, dtype=torch.int32, device=dev)
+    best_trial = torch.empty(1, dtype=torch.int32, device=dev)
+    per_trial = torch.empty(trials, dtype=torch.int32, device=dev) if want_per_trial else None
+    if sample_idx is not None:
+        sample_idx = sample_idx.to(device=dev, dtype=torch.int32).contiguous()
+        assert tuple(sample_idx.shape) == (trials, min_samples)
+    nbytes = load().pm_ransac_workspace_bytes(trials)
+    ws = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=dev)
+    check(load().pm_ransac_affine(ptr(moving_k), ptr(fixed_k), k, ptr(sample_idx), trials, min_samples, float(error),
+                                  int(seed) & (2 ** 64 - 1), ptr(best_a), ptr(best_inl), ptr(best_trial),
+                                  ptr(per_trial), ptr(ws), nbytes, stream_ptr()), "pm_ransac_affine")
+    return best_a, best_inl, best_trial, per_trial
+
+
+def icp_affine(moving, fixed, iterations=50, want_nn=False):
+    """-> (A_icp [16] f64, residuals [iterations] f64, nn [N1] i32 | None)."""
+    torch = _torch()
+    n1, n2, dev = moving.shape[0], fixed.shape[0], moving.device
+    a_icp = torch.empty(16, dtype=torch.float64, device=dev)
+    resid = torch.empty(max(iterations, 1), dtype=torch.float64, device=dev)
+    nn = torch.empty(n1, dtype=torch.int32, device=dev) if want_nn else None
+    nbytes = load().pm_icp_workspace_bytes(n1)
+    ws = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=dev)
+    check(load().pm_icp_affine(ptr(moving), n1, ptr(fixed), n2, int(iterations), ptr(a_icp), ptr(resid), ptr(nn),
+                               ptr(ws), nbytes, stream_ptr()), "pm_icp_affine")
+    return a_icp, resid[:iterations], nn
+
+
+def fit_affine(moving_k, fixed_k):
+    torch = _torch()
+    a = torch.empty(16, dtype=torch.float64, device=moving_k.device)
+    check(load().pm_fit_affine(ptr(moving_k), ptr(fixed_k), moving_k.shape[0], ptr(a), stream_ptr()), "pm_fit_affine")
+    return a
+
+
+def apply_affine(pts, a16):
+    torch = _torch()
+    out = torch.empty_like(pts)
+    check(load().pm_apply_affine(ptr(pts), pts.shape[0], ptr(a16), ptr(out), stream_ptr()), "pm_apply_affine")
+    return out
+
+
+def gather_points(pts, index_i32):
+    torch = _torch()
+    k = index_i32.numel()
+    out = torch.empty((k, 3), dtype=torch.float64, device=pts.device)
+    check(load().pm_gather_points(ptr(pts), ptr(index_i32), k, ptr(out), stream_ptr()), "pm_gather_points")
+    return out
+
+
+def compose(a16, b16):
+    torch = _torch()
+    c = torch.empty(16, dtype=torch.float64, device=a16.device)
+    check(load().pm_compose(ptr(a16), ptr(b16), ptr(c), stream_ptr()), "pm_compose")
+    return c

@@ -1,0 +1,46 @@
+"""GPU replacement for `scipy.optimize.linear_sum_assignment` as used at reference
+_dock_widget.py:604-611 (same return convention: rows ascending, min(nr, nc) pairs)."""
+import numpy as np
+
+from . import device as D
+
+__all__ = ["linear_sum_assignment"]
+
+
+def linear_sum_assignment(cost_matrix, maximize=False, return_stats=False, max_bid_rounds=128):
+    """Minimum-cost assignment of a dense (nr, nc) matrix -> (row_ind, col_ind) int64 arrays.
+
+    The matrix is solved as float32 values with float64 duals (optimal for the float32-rounded
+    matrix).  Tall matrices are solved through the transpose, as scipy does.
+    """
+    torch = D._torch()
+    c = np.asarray(cost_matrix)
+    if c.ndim != 2:
+        raise ValueError("expected a matrix (2-D array), got a %d array" % c.ndim)
+    if c.size == 0:
+        z = np.zeros(0, dtype=np.int64)
+        return (z, z, {}) if return_stats else (z, z)
+    if not np.all(np.isfinite(c)):
+        raise ValueError("matrix contains invalid numeric entries")
+    if maximize:
+        c = -c
+    transposed = c.shape[0] > c.shape[1]
+    if transposed:
+        c = c.T
+    nr, nc = c.shape
+    ldc = (nc + 3) // 4 * 4
+    buf = np.zeros((1, nr, ldc), dtype=np.float32)
+    buf[0, :, :nc] = c
+    col4row, total, stats = D.lap_solve(torch.from_numpy(buf).cuda(), nr, nc, max_bid_rounds)
+    col = col4row[0].cpu().numpy().astype(np.int64)
+    st = stats[0].cpu().numpy()
+    if st[4] != 0:
+        raise ValueError("cost matrix is infeasible")
+    rows = np.arange(nr, dtype=np.int64)
+    if transposed:
+        order = np.argsort(col)
+        rows, col = col[order], rows[order]
+    if return_stats:
+        return rows, col, dict(total=float(total.item()), bid_rounds=int(st[0]), rows_after_bidding=int(st[1]),
+                               augmentations=int(st[2]), dijkstra_steps=int(st[3]))
+    return rows, col

@@ -1,0 +1,350 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs,
+against the golden vectors dumped from the reference, and — at BASELINE.json's full sizes — through
+size-independent properties.  Bars (BASELINE.json north_star): integer histograms bit-exact; cost
+matrix within 1e-5 relative; equal optimal assignment cost (identical assignment where unique);
+final 4x4 within 1e-4.
+"""
+import numpy as np
+import pytest
+
+from conftest import HYP_TAGS, UNARY_KEYS, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    torch.cuda.set_device(0)
+    return torch
+
+
+@pytest.fixture(scope="module")
+def D(torch):
+    from platymatch_b200 import device
+    return device
+
+
+def _pair(n, seed=None):
+    from platymatch_b200.synthetic import make_pair
+    return make_pair(n, seed=seed)
+
+
+# ------------------------------------------------------------------------------ K0 / K1
+@pytest.mark.parametrize("n", [2, 3, 31, 257, 3000])
+def test_centroid_axis_mean_distance(O, D, torch, n):
+    rng = np.random.default_rng(n)
+    pts = rng.normal(size=(n, 3)) * np.array([30.0, 20.0, 10.0]) + np.array([300.0, 200.0, 100.0])
+    d = torch.from_numpy(pts).cuda()
+    stats = D.cloud_stats(d).cpu().numpy()
+    assert np.allclose(stats[0:3], pts.mean(0), rtol=1e-13)
+    md = D.mean_distance(d).item()
+    assert md == pytest.approx(O.get_mean_distance(pts, True), rel=1e-12)
+    if n >= 31:
+        x0 = O.pca_first_axis(pts)
+        assert np.allclose(stats[3:6], x0, atol=1e-10)
+
+
+def test_api_utils_match_reference_goldens(torch):
+    from platymatch_b200.utils.utils import get_centroid, get_mean_distance, get_error
+    g = load_golden("asset02")
+    assert np.allclose(get_centroid(g["moving"], transposed=False), g["moving_centroid"], rtol=1e-13)
+    assert get_centroid(g["moving"].T, transposed=True).shape == (1, 3)
+    assert get_mean_distance(g["fixed"], transposed=False) == pytest.approx(float(g["fixed_mean_distance"]), rel=1e-12)
+    assert get_error(g["moving"], g["moving"]) == 0.0
+    # test_utils.py:5-8 of the reference: centroid of the unit cube
+    cube = np.array([[0, 0, 0], [0, 0, 1], [0, 1, 0], [0, 1, 1], [1, 0, 0], [1, 0, 1], [1, 1, 0], [1, 1, 1]], dtype=float)
+    assert np.allclose(get_centroid(cube, transposed=True), [[0.5, 0.5, 0.5]])
+
+
+# ------------------------------------------------------------------------------ K2
+def test_shape_context_bit_exact_vs_reference_goldens(torch, golden):
+    """get_unary on the reference's assets: integer histograms of all 6 descriptor sets bit-exact."""
+    from platymatch_b200.estimate_transform.shape_context import get_unary, get_unary_counts
+    for cloud, typ, keys in (("moving", "moving", ["u11", "u12"]), ("fixed", "fixed", ["u21", "u22", "u23", "u24"])):
+        counts, dropped, ties, x0 = get_unary_counts(golden[cloud + "_centroid"], float(golden[cloud + "_mean_distance"]),
+                                                     golden[cloud], typ)
+        for v, k in enumerate(keys):
+            assert np.array_equal(counts[v], golden["counts_" + k].astype(np.uint32)), (golden["name"], k)
+            assert np.array_equal(dropped[v], golden[cloud].shape[1] - 1 - golden["totals_" + k])
+        sc = get_unary(golden[cloud + "_centroid"], float(golden[cloud + "_mean_distance"]), golden[cloud], typ)
+        assert len(sc) == 4 and sc[0].shape == (golden[cloud].shape[1], 360)
+        if typ == "moving":
+            assert sc[2].size == 0 and sc[3].size == 0
+        for v, k in enumerate(keys):
+            assert np.array_equal(sc[v][:8], golden["sc_rows_" + k])      # float64 rows, bit for bit
+
+
+@pytest.mark.parametrize("n", [2, 5, 33, 1000, 3000])
+def test_shape_context_bit_exact_vs_oracle(O, torch, n):
+    from platymatch_b200.estimate_transform.shape_context import get_unary_counts
+    p = _pair(max(n, 4), seed=100 + n)
+    pts = p["fixed"][:, :n]
+    c, md = O.get_centroid(pts, False), (O.get_mean_distance(pts, False) if n > 1 else 1.0)
+    counts, dropped, ties, x0 = get_unary_counts(c, md, pts, "fixed")
+    for v in range(4):
+        oc, od = O.shape_context_counts(pts.T, c, md, x0, v + 1)
+        assert np.array_equal(counts[v], oc), (n, v, int(np.abs(counts[v].astype(int) - oc.astype(int)).sum()))
+        assert np.array_equal(dropped[v], od)
+    assert np.allclose(x0, O.pca_first_axis(pts.T), atol=1e-9) or n < 10
+
+
+def test_shape_context_edge_cases(O, torch):
+    """Coincident nuclei (NaN -> dropped), theta == pi and theta == 0 neighbours, integer coordinates."""
+    from platymatch_b200.estimate_transform.shape_context import get_unary_counts
+    rng = np.random.default_rng(5)
+    pts = np.round(rng.normal(size=(3, 200)) * 40 + 200)          # integer grid -> many exact ties
+    pts[:, 10] = pts[:, 11]                                       # coincident pair
+    c = O.get_centroid(pts, False)
+    pts[:, 20] = c[:, 0] + 2.0 * (pts[:, 21] - c[:, 0])           # collinear with the centroid: theta = 0 / pi
+    md = O.get_mean_distance(pts, False)
+    counts, dropped, ties, x0 = get_unary_counts(c, md, pts, "fixed")
+    for v in range(4):
+        oc, od = O.shape_context_counts(pts.T, c, md, x0, v + 1)
+        assert np.array_equal(counts[v], oc)
+        assert np.array_equal(dropped[v], od)
+    assert dropped[0][10] >= 1 and dropped[0][11] >= 1
+
+
+def test_variants_are_phi_permutations(torch):
+    """sc2/sc3/sc4 are phi-bin permutations of sc (no ties on generic float data)."""
+    from platymatch_b200.estimate_transform.shape_context import get_unary_counts
+    g = load_golden("synth400")
+    counts, _, _, _ = get_unary_counts(g["fixed_centroid"], float(g["fixed_mean_distance"]), g["fixed"], "fixed")
+    h = counts.reshape(4, -1, 30, 12)
+    k = np.arange(12)
+    assert np.array_equal(h[1][:, :, (k + 6) % 12], h[0])
+    assert np.array_equal(h[2][:, :, 11 - k], h[0])
+    assert np.array_equal(h[3][:, :, (5 - k) % 12], h[0])
+
+
+# ------------------------------------------------------------------------------ K3
+def test_chi2_vs_reference_goldens(torch, golden):
+    """cost matrix within 1e-5 relative of the reference's float64 matrices."""
+    from platymatch_b200.estimate_transform.shape_context import unary_distance_matrix, get_unary
+    um = get_unary(golden["moving_centroid"], float(golden["moving_mean_distance"]), golden["moving"], "moving")
+    uf = get_unary(golden["fixed_centroid"], float(golden["fixed_mean_distance"]), golden["fixed"], "fixed")
+    u = {"u11": um[0], "u12": um[1], "u21": uf[0], "u22": uf[1], "u23": uf[2], "u24": uf[3]}
+    worst = 0.0
+    for tag in HYP_TAGS:
+        ka, kb = UNARY_KEYS[tag]
+        U = unary_distance_matrix(u[ka], u[kb])
+        sub = golden["cost_sub_" + tag]
+        ref = golden["cost_full_" + tag] if "cost_full_" + tag in golden else sub
+        got = U[:ref.shape[0]]
+        nz = ref > 0
+        worst = max(worst, float((np.abs(got - ref)[nz] / ref[nz]).max()))
+        assert np.all(got[~nz] == 0.0)                      # identical histograms -> exactly 0, like the reference
+    assert worst < 1e-5, worst
+
+
+@pytest.mark.parametrize("n1,n2", [(1, 1), (3, 130), (129, 127), (700, 900)])
+def test_chi2_vs_oracle_shapes(O, torch, n1, n2):
+    from platymatch_b200.estimate_transform.shape_context import unary_distance_matrix, get_unary_distance
+    rng = np.random.default_rng(n1 * 1000 + n2)
+    def hist(n):
+        c = rng.poisson(0.6, size=(n, 360)).astype(np.float64) * (rng.random((n, 360)) < 0.4)
+        c[:, 0] += 1
+        return c / c.sum(1, keepdims=True)
+    a, b = hist(n1), hist(n2)
+    U, ref = unary_distance_matrix(a, b), O.unary_distance_matrix(a, b)
+    assert U.shape == (n1, n2)
+    assert np.allclose(U, ref, rtol=1e-5, atol=0)
+    assert get_unary_distance(a[0], b[0]) == pytest.approx(ref[0, 0], rel=1e-5)
+    assert get_unary_distance(a[0], a[0]) == 0.0
+
+
+# ------------------------------------------------------------------------------ K4
+def _check_lap(O, cost, **kw):
+    from platymatch_b200.lap import linear_sum_assignment
+    from scipy.optimize import linear_sum_assignment as scipy_lsa
+    c32 = np.asarray(cost, dtype=np.float32).astype(np.float64)          # the values the GPU solves
+    r, c, st = linear_sum_assignment(cost, return_stats=True, **kw)
+    ro, co = O.linear_sum_assignment(c32)
+    rs, cs = scipy_lsa(c32)
+    assert np.array_equal(ro, rs) and np.array_equal(co, cs)             # oracle == scipy on the same matrix
+    assert len(np.unique(c)) == len(c) == min(cost.shape) and np.array_equal(r, np.sort(r))
+    got, ref = c32[r, c].sum(), c32[ro, co].sum()
+    assert got == pytest.approx(ref, rel=1e-12, abs=1e-12), (got, ref, st)
+    assert st["total"] == pytest.approx(ref, rel=1e-12, abs=1e-12)
+    return (r, c), (ro, co), st
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 7), (2, 2), (5, 9), (9, 5), (64, 64), (100, 257), (300, 300), (500, 1200)])
+@pytest.mark.parametrize("rounds", [0, 3, 128])
+def test_lap_random_matrices(O, torch, shape, rounds):
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    cost = rng.random(shape)
+    (r, c), (ro, co), st = _check_lap(O, cost, max_bid_rounds=rounds)
+    assert np.array_equal(c, co)              # continuous random costs: the optimum is unique
+
+
+def test_lap_ties_and_structure(O, torch):
+    """Integer costs (many equal-cost optima), constant matrix, permuted diagonal, negative entries."""
+    rng = np.random.default_rng(3)
+    _check_lap(O, rng.integers(0, 5, size=(60, 80)).astype(float))
+    _check_lap(O, np.ones((17, 17)))
+    perm = rng.permutation(200)
+    cost = np.ones((200, 200)); cost[np.arange(200), perm] = 0.0
+    (r, c), _, _ = _check_lap(O, cost)
+    assert np.array_equal(c, perm)
+    _check_lap(O, rng.normal(size=(50, 70)))
+
+
+def test_lap_on_reference_cost_matrices(O, torch):
+    """The assignment scipy produced inside the reference run (golden) is reproduced on the same matrix."""
+    from platymatch_b200.lap import linear_sum_assignment
+    g = load_golden("synth400")
+    for tag in ["11", "12", "13", "14"]:
+        U = g["cost_full_" + tag]
+        r, c = linear_sum_assignment(U)
+        c32 = U.astype(np.float32).astype(np.float64)
+        assert c32[r, c].sum() == pytest.approx(c32[g["lap_row_" + tag], g["lap_col_" + tag]].sum(), rel=1e-9)
+        assert U[r, c].sum() == pytest.approx(float(g["lap_cost_" + tag]), rel=1e-6)
+        assert np.mean(c == g["lap_col_" + tag]) > 0.98      # float32 rounding may move near-ties only
+
+
+def test_lap_3k_pair_equal_cost(O, torch):
+    """Config 1 size (2700 x 3000): equal optimal cost and identical assignment vs the oracle on the GPU's matrix."""
+    import platymatch_b200 as pm
+    p = _pair(3000)
+    dm, df = pm.describe_cloud(p["moving"], 1), pm.describe_cloud(p["fixed"], 4)
+    res = pm.register_described(dm, df, ransac_trials=64, icp_iterations=1, keep_cost=True)
+    cost = res["cost"].cpu().numpy()[:, :, :3000].astype(np.float64)
+    for q in range(4):
+        ro, co = O.linear_sum_assignment(cost[q])
+        got = res["assignments"][q][1].cpu().numpy()
+        assert res["lap_cost"][q].item() == pytest.approx(cost[q][ro, co].sum(), rel=1e-12)
+        assert np.array_equal(got, co), q
+
+
+# ------------------------------------------------------------------------------ K5
+def test_ransac_vs_reference_goldens(O, torch, golden):
+    from platymatch_b200.estimate_transform.shape_context import do_ransac
+    m, f = golden["moving"], golden["fixed"]
+    rs = np.random.RandomState(int(golden["seed"]))
+    trials = int(golden["trials"])
+    for q, tag in enumerate(HYP_TAGS):
+        r, c = golden["lap_row_" + tag], golden["lap_col_" + tag]
+        idx = np.stack([rs.choice(len(r), 4, replace=False) for _ in range(trials)])
+        A, inl = do_ransac(m[:, r], f[:, c], 4, trials, 16, 'Affine', sample_indices=idx)
+        assert inl == int(golden["ransac_inliers"][q]), tag
+        assert np.allclose(A, golden["ransac_A"][q], rtol=1e-7, atol=1e-7), tag
+
+
+def test_ransac_per_trial_counts_and_device_rng(O, D, torch):
+    p = _pair(800, seed=8)
+    k = p["moving"].shape[1]
+    m, f = p["moving"], p["fixed"][:, p["gt_fixed_index"]]
+    idx = O.ransac_sample_indices(k, 4, 300, seed=4)
+    _, _, inl_o, mats = O.do_ransac(m, f, 4, 300, 16, sample_indices=idx, return_all=True)
+    md, fd = D.to_device_points(m), D.to_device_points(f)
+    a, inl, trial, per = D.ransac_affine(md, fd, 300, 16.0, 4, torch.from_numpy(idx).cuda(), want_per_trial=True)
+    assert np.array_equal(per.cpu().numpy(), inl_o)
+    assert trial.item() == int(np.argmax(inl_o))
+    # device Philox sampling: deterministic per seed, indices distinct, finds the true affine on clean matches
+    a1, i1, _, _ = D.ransac_affine(md, fd, 500, 16.0, 4, None, seed=123)
+    a2, i2, _, _ = D.ransac_affine(md, fd, 500, 16.0, 4, None, seed=123)
+    assert i1.item() == i2.item() and torch.equal(a1, a2) and i1.item() > 0.9 * k
+    # no inliers at all -> all-ones matrix and 0, as the reference (shape_context.py:120)
+    far = torch.from_numpy(np.random.default_rng(0).normal(size=(50, 3)) * 1e6).cuda()
+    a0, i0, t0, _ = D.ransac_affine(md[:50].contiguous(), far, 20, 1e-3, 4, None, seed=1)
+    assert i0.item() == 0 and torch.all(a0 == 1.0)
+
+
+# ------------------------------------------------------------------------------ K6 + small ops
+def test_icp_vs_reference_goldens(torch, golden):
+    from platymatch_b200.estimate_transform.apply_transform import apply_affine_transform
+    from platymatch_b200.estimate_transform.perform_icp import perform_icp
+    moved = apply_affine_transform(golden["moving"], golden["A_sc"])
+    a_icp, resid = perform_icp(moved, golden["fixed"], 50, 'Affine', verbose=False, return_residuals=True)
+    assert np.allclose(a_icp, golden["A_icp"], rtol=1e-7, atol=1e-7)
+    assert np.allclose(resid, golden["icp_residuals"], rtol=1e-6, atol=1e-9)
+    assert np.abs(a_icp @ golden["A_sc"] - golden["A_final"]).max() < 1e-4
+
+
+def test_icp_nearest_neighbour_map(O, D, torch):
+    p = _pair(1500, seed=2)
+    m = O.apply_affine_transform(p["moving"], p["A_gt"])
+    _, _, nn = D.icp_affine(D.to_device_points(m), D.to_device_points(p["fixed"]), 1, want_nn=True)
+    nn_o, _ = O.nearest(m, p["fixed"])
+    assert np.array_equal(nn.cpu().numpy(), nn_o)
+
+
+def test_fit_apply_compose(O, torch, golden):
+    from platymatch_b200.estimate_transform.find_transform import get_affine_transform
+    from platymatch_b200.estimate_transform.apply_transform import apply_affine_transform
+    m, f = golden["moving"], golden["fixed"]
+    assert np.allclose(get_affine_transform(m[:, :50], f[:, :50]), O.get_affine_transform(m[:, :50], f[:, :50]),
+                       rtol=1e-8, atol=1e-8)
+    assert np.allclose(apply_affine_transform(m, golden["A_gt"]), O.apply_affine_transform(m, golden["A_gt"]),
+                       rtol=1e-14, atol=1e-12)
+    m4 = np.vstack([m, np.ones((1, m.shape[1]))])
+    assert np.allclose(apply_affine_transform(m4, golden["A_gt"]), O.apply_affine_transform(m, golden["A_gt"]))
+
+
+# ------------------------------------------------------------------------------ pipeline
+def test_pipeline_vs_reference_goldens(O, torch, golden):
+    """Full unsupervised registration on the reference's inputs with the reference's RNG stream."""
+    import platymatch_b200 as pm
+    rs = np.random.RandomState(int(golden["seed"]))
+    trials = int(golden["trials"])
+    k = min(golden["moving"].shape[1], golden["fixed"].shape[1])
+    idx = [np.stack([rs.choice(k, 4, replace=False) for _ in range(trials)]) for _ in range(8)]
+    res = pm.estimate_transform_unsupervised(golden["moving"], golden["fixed"], ransac_trials=trials,
+                                             sample_indices=idx, as_reference=True)
+    assert res["inliers"].tolist() == golden["ransac_inliers"].tolist()
+    assert res["best"] == int(golden["best"])
+    assert np.abs(res["transform"] - golden["A_final"]).max() < 1e-4
+    if golden["name"].startswith("asset"):      # reference's own known-answer assertion
+        np.testing.assert_array_almost_equal(golden["A_gt"], res["transform"])
+    for q, tag in enumerate(HYP_TAGS):
+        assert np.array_equal(res["assignments"][q][1], golden["lap_col_" + tag]), tag
+
+
+def test_pipeline_supervised_vs_reference_goldens(torch):
+    import platymatch_b200 as pm
+    for name in ("asset02", "synth400"):
+        g = load_golden(name)
+        res = pm.estimate_transform_supervised(g["moving"], g["fixed"], g["kp_moving"], g["kp_fixed"])
+        assert np.allclose(res["transform_sc"], g["A_kp"], rtol=1e-7, atol=1e-7)
+        assert np.abs(res["transform"] - g["A_kp_icp"] @ g["A_kp"]).max() < 1e-4
+
+
+def test_pipeline_tall_problem(O, torch):
+    """More moving than fixed nuclei: solved through the transpose like scipy, pairs ordered by moving index."""
+    import platymatch_b200 as pm
+    p = _pair(500, seed=9)
+    moving, fixed = p["fixed"], p["moving"]        # swap roles: N1 = 500 > N2 = 450
+    idx = [O.ransac_sample_indices(450, 4, 200, seed=q) for q in range(4)]
+    res = pm.estimate_transform_unsupervised(moving, fixed, ransac_trials=200, sample_indices=idx)
+    ref = O.estimate_transform_unsupervised(moving, fixed, ransac_trials=200, hypotheses=O.HYPOTHESES[:4], sample_indices=idx)
+    assert res["best"] == ref["best"]
+    assert np.allclose(res["lap_cost"], ref["lap_cost"], rtol=1e-5)
+    assert np.abs(res["transform"] - ref["transform"]).max() < 1e-4
+
+
+def test_full_size_properties_8k(O, torch):
+    """BASELINE config 2 (8k x 8k): properties that do not need the reference (27 h on the CPU).
+
+    - histogram rows count N-1-dropped neighbours; variants are phi permutations of each other;
+    - the LAP result is a valid assignment whose duals certify optimality is not re-derived here, but its
+      cost must not exceed the ground-truth matching's cost and must equal the oracle's on the same matrix
+      for the true hypothesis (one 7200 x 8000 CPU solve, a few seconds);
+    - the recovered transform maps moving nuclei onto their true partners (median error < jitter scale).
+    """
+    import platymatch_b200 as pm
+    p = _pair(8000)
+    res = pm.estimate_transform_unsupervised(p["moving"], p["fixed"], ransac_trials=2000, keep_cost=True, seed=1)
+    best = res["best"]
+    cost = res["cost"][best][:, :8000].astype(np.float64)
+    mov_idx, fix_idx = res["assignments"][best]
+    assert len(np.unique(fix_idx)) == len(fix_idx) == 7200
+    gt_cost = cost[np.arange(7200), p["gt_fixed_index"]].sum()
+    assert res["lap_cost"][best] <= gt_cost + 1e-9
+    ro, co = O.linear_sum_assignment(cost)
+    assert res["lap_cost"][best] == pytest.approx(cost[ro, co].sum(), rel=1e-12)
+    moved = O.apply_affine_transform(p["moving"], res["transform"])
+    err = np.linalg.norm(moved - p["fixed"][:, p["gt_fixed_index"]], axis=0)
+    assert np.median(err) < 4.0, np.median(err)
+    assert res["inliers"][best] > 3 * np.delete(res["inliers"], best).max()
