@@ -20,7 +20,10 @@
 // Costs are the float32 matrix produced by K3; duals, distances and the total are float64, so the
 // result is optimal for the matrix given (up to float64 rounding, like scipy on the same values).
 #include <limits.h>
+#include <cooperative_groups.h>
 #include "pm_common.cuh"
+
+namespace cg = cooperative_groups;
 
 #define PM_LAP_BID_THREADS 256
 #define PM_LAP_CPT 8
@@ -33,10 +36,9 @@ struct PmLapView {
     int32_t *col4row;       // [nr]  (caller's output buffer)
     int32_t *bid_col;       // [nr]
     double *bid_gamma;      // [nr]
-    unsigned long long *colbest;  // [nc]
-    int32_t *colwin;        // [nc]
-    int32_t *free_a, *free_b;     // [nr] each
-    int32_t *counters;      // [0] count_a, [1] count_b, [2] rounds run, [3] status
+    unsigned long long *colbest;  // [nc] winning bid key of the round (0 = no bid)
+    int32_t *free_lists;    // [3][nr] rotating free-row lists
+    int32_t *counters;      // [0..2] list counts, [3] bid rounds run, [4] status
     long long *stats;       // [PM_LAP_STATS] or null
     double *total;
 };
@@ -44,7 +46,7 @@ struct PmLapView {
 static inline size_t pm_lap_align(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct PmLapLayout {
-    size_t u, v, row4col, bid_col, bid_gamma, colbest, colwin, free_a, free_b, counters, per_item;
+    size_t u, v, row4col, bid_col, bid_gamma, colbest, free_lists, counters, per_item;
 };
 
 static PmLapLayout pm_lap_layout(int nr, int nc) {
@@ -56,18 +58,17 @@ static PmLapLayout pm_lap_layout(int nr, int nc) {
     L.bid_col = o; o += pm_lap_align((size_t)nr * 4);
     L.bid_gamma = o; o += pm_lap_align((size_t)nr * 8);
     L.colbest = o; o += pm_lap_align((size_t)nc * 8);
-    L.colwin = o; o += pm_lap_align((size_t)nc * 4);
-    L.free_a = o; o += pm_lap_align((size_t)nr * 4);
-    L.free_b = o; o += pm_lap_align((size_t)nr * 4);
+    L.free_lists = o; o += pm_lap_align((size_t)nr * 4 * 3);
     L.counters = o; o += pm_lap_align(16 * 4);
     L.per_item = o;
     return L;
 }
 
 struct PmLapBatch {   // passed by value to kernels
-    const float *cost; size_t cost_stride; int nr, nc, ldc;
+    const float *cost; size_t cost_stride; int nr, nc, ncp, ldc;
     char *ws; PmLapLayout L;
     int32_t *col4row; long long *stats; double *total;
+    int32_t *progress;   // [2] assignments made in the current / previous bidding round
 };
 
 __device__ __forceinline__ PmLapView pm_lap_view(const PmLapBatch &B, int b) {
@@ -78,8 +79,8 @@ __device__ __forceinline__ PmLapView pm_lap_view(const PmLapBatch &B, int b) {
     V.row4col = (int32_t *)(w + B.L.row4col);
     V.col4row = B.col4row + (size_t)b * B.nr;
     V.bid_col = (int32_t *)(w + B.L.bid_col); V.bid_gamma = (double *)(w + B.L.bid_gamma);
-    V.colbest = (unsigned long long *)(w + B.L.colbest); V.colwin = (int32_t *)(w + B.L.colwin);
-    V.free_a = (int32_t *)(w + B.L.free_a); V.free_b = (int32_t *)(w + B.L.free_b);
+    V.colbest = (unsigned long long *)(w + B.L.colbest);
+    V.free_lists = (int32_t *)(w + B.L.free_lists);
     V.counters = (int32_t *)(w + B.L.counters);
     V.stats = B.stats ? B.stats + (size_t)b * PM_LAP_STATS : nullptr;
     V.total = B.total + b;
@@ -90,10 +91,11 @@ __device__ __forceinline__ PmLapView pm_lap_view(const PmLapBatch &B, int b) {
 __global__ void pm_lap_init_kernel(PmLapBatch B) {
     const PmLapView V = pm_lap_view(B, blockIdx.y);
     const int t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    for (int i = t; i < B.nr; i += stride) { V.u[i] = 0.0; V.col4row[i] = -1; V.free_a[i] = i; V.bid_col[i] = -1; }
-    for (int j = t; j < B.nc; j += stride) { V.v[j] = 0.0; V.row4col[j] = -1; V.colbest[j] = 0ull; V.colwin[j] = INT_MAX; }
+    for (int i = t; i < B.nr; i += stride) { V.u[i] = 0.0; V.col4row[i] = -1; V.free_lists[i] = i; V.bid_col[i] = -1; }
+    for (int j = t; j < B.ncp; j += stride) { V.v[j] = 0.0; V.row4col[j] = -1; V.colbest[j] = 0ull; }
     if (t == 0) {
-        V.counters[0] = B.nr; V.counters[1] = 0; V.counters[2] = 0; V.counters[3] = 0;
+        V.counters[0] = B.nr; V.counters[1] = 0; V.counters[2] = 0; V.counters[3] = 0; V.counters[4] = 0;
+        B.progress[0] = 0; B.progress[1] = 0;
         if (V.stats) for (int k = 0; k < PM_LAP_STATS; ++k) V.stats[k] = 0;
     }
 }
@@ -110,99 +112,114 @@ __device__ __forceinline__ void pm_bid_merge(PmBid &a, double w1, double w2, int
     else a.w2 = fmin(a.w2, w1);
 }
 
-// One CTA per free row (grid-stride over the free list).  parity selects the current list.
-__global__ void __launch_bounds__(PM_LAP_BID_THREADS) pm_lap_bid_kernel(PmLapBatch B, int parity) {
-    const PmLapView V = pm_lap_view(B, blockIdx.y);
-    const int nfree = V.counters[parity];
-    const int32_t *list = parity ? V.free_b : V.free_a;
+// Winner selection key of a bid: float32 image of the increment (monotone in gamma) in the high
+// word, ~row in the low word -> atomicMax picks the largest increment, ties to the lowest row.
+// ANY bidder may win without hurting exactness: the winner lowers the price by its OWN float64
+// gamma, which makes its edge tight against its own second-best column.
+__device__ __forceinline__ unsigned long long pm_bid_key(double gamma, int row) {
+    return ((unsigned long long)__float_as_uint(__double2float_rd(gamma)) << 32) |
+           (unsigned long long)(0xffffffffu - (unsigned)row);
+}
+
+// Persistent cooperative kernel: all rounds of the parallel bidding for all matrices of the batch.
+// Per round: (A) every free row is scanned by one CTA and bids; grid barrier; (B) winners take
+// their columns, everybody else goes to the next free list; grid barrier.  Three rotating list
+// counters (current / next / stale-to-zero) avoid any reset race.  Stops when no row is free, when a
+// round assigns nothing (only zero-increment steals left), or after max_rounds.
+__global__ void __launch_bounds__(PM_LAP_BID_THREADS) pm_lap_bid_persistent(PmLapBatch B, int batch, int max_rounds) {
+    cg::grid_group grid = cg::this_grid();
     __shared__ double s_w1[PM_LAP_BID_THREADS / 32], s_w2[PM_LAP_BID_THREADS / 32];
     __shared__ int s_j1[PM_LAP_BID_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int idx = blockIdx.x; idx < nfree; idx += gridDim.x) {
-        const int i = list[idx];
-        const float *ci = V.cost + (size_t)i * B.ldc;
-        PmBid bid = {INFINITY, INFINITY, INT_MAX};
-        for (int j = threadIdx.x * 4; j < B.nc; j += PM_LAP_BID_THREADS * 4) {
-            const float4 c4 = *reinterpret_cast<const float4 *>(ci + j);   // ldc % 4 == 0, pad readable
-            const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    int round = 0;
+    for (; round < max_rounds; ++round) {
+        const int cur = round % 3, nxt = (round + 1) % 3, old = (round + 2) % 3;
+        // ---- phase A: bids.  Work item = (matrix b, position idx in its free list)
+        int total_free = 0;
+        for (int b = 0; b < batch; ++b) {
+            const PmLapView V = pm_lap_view(B, b);
+            const int nfree = __ldcg(&V.counters[cur]);
+            const int32_t *list = V.free_lists + (size_t)cur * B.nr;
+            // CTA c takes items (c - total_free) mod gridDim of this matrix, so matrices interleave over CTAs
+            int first = (int)blockIdx.x - (total_free % (int)gridDim.x);
+            if (first < 0) first += gridDim.x;
+            for (int idx = first; idx < nfree; idx += gridDim.x) {
+                const int i = __ldcg(&list[idx]);
+                const float *ci = V.cost + (size_t)i * B.ldc;
+                PmBid bid = {INFINITY, INFINITY, INT_MAX};
+                for (int j = threadIdx.x * 4; j < B.nc; j += PM_LAP_BID_THREADS * 4) {
+                    const float4 c4 = *reinterpret_cast<const float4 *>(ci + j);   // ldc % 4 == 0, pad readable
+                    const double2 va = __ldcg(reinterpret_cast<const double2 *>(V.v + j));
+                    const double2 vb = __ldcg(reinterpret_cast<const double2 *>(V.v + j + 2));
+                    if (j + 0 < B.nc) pm_bid_push(bid, (double)c4.x - va.x, j + 0);
+                    if (j + 1 < B.nc) pm_bid_push(bid, (double)c4.y - va.y, j + 1);
+                    if (j + 2 < B.nc) pm_bid_push(bid, (double)c4.z - vb.x, j + 2);
+                    if (j + 3 < B.nc) pm_bid_push(bid, (double)c4.w - vb.y, j + 3);
+                }
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (j + q < B.nc) pm_bid_push(bid, (double)cc[q] - V.v[j + q], j + q);
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ow1 = __shfl_xor_sync(0xffffffffu, bid.w1, o), ow2 = __shfl_xor_sync(0xffffffffu, bid.w2, o);
+                    const int oj = __shfl_xor_sync(0xffffffffu, bid.j1, o);
+                    pm_bid_merge(bid, ow1, ow2, oj);
+                }
+                __syncthreads();
+                if (lane == 0) { s_w1[warp] = bid.w1; s_w2[warp] = bid.w2; s_j1[warp] = bid.j1; }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    PmBid tot = {s_w1[0], s_w2[0], s_j1[0]};
+                    for (int w = 1; w < PM_LAP_BID_THREADS / 32; ++w) pm_bid_merge(tot, s_w1[w], s_w2[w], s_j1[w]);
+                    // nc == 1: no second best; an unowned single column is simply taken with gamma 0
+                    double gamma = (tot.w2 == INFINITY) ? 0.0 : tot.w2 - tot.w1;
+                    if (!(gamma > 0.0)) gamma = 0.0;
+                    int j1 = tot.j1;
+                    if (j1 == INT_MAX || tot.w1 == INFINITY) j1 = -1;                    // all-inf row: phase 2 reports it
+                    else if (gamma == 0.0 && __ldcg(&V.row4col[j1]) >= 0) j1 = -1;       // zero-increment steal: wait
+                    V.bid_col[i] = j1;
+                    V.bid_gamma[i] = gamma;
+                    if (j1 >= 0) atomicMax(&V.colbest[j1], pm_bid_key(gamma, i));
+                }
+            }
+            total_free += nfree;
+            if (gtid == 0) V.counters[old] = 0;        // consumed in the previous round
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ow1 = __shfl_xor_sync(0xffffffffu, bid.w1, o), ow2 = __shfl_xor_sync(0xffffffffu, bid.w2, o);
-            const int oj = __shfl_xor_sync(0xffffffffu, bid.j1, o);
-            pm_bid_merge(bid, ow1, ow2, oj);
+        if (gtid == 0) B.progress[round & 1] = 0;
+        if (total_free == 0) break;                    // uniform: every CTA read the same counters
+        grid.sync();
+        // ---- phase B: winners take their columns; everybody else (and displaced owners) -> next list
+        for (int b = 0; b < batch; ++b) {
+            const PmLapView V = pm_lap_view(B, b);
+            const int nfree = __ldcg(&V.counters[cur]);
+            const int32_t *list = V.free_lists + (size_t)cur * B.nr;
+            int32_t *next = V.free_lists + (size_t)nxt * B.nr;
+            int32_t *next_count = &V.counters[nxt];
+            for (int idx = gtid; idx < nfree; idx += gthreads) {
+                const int i = __ldcg(&list[idx]), j = __ldcg(&V.bid_col[i]);
+                bool won = false;
+                if (j >= 0) {
+                    const double gamma = __ldcg(&V.bid_gamma[i]);
+                    won = __ldcg(&V.colbest[j]) == pm_bid_key(gamma, i);
+                    if (won) {
+                        const int prev = __ldcg(&V.row4col[j]);
+                        const double vj = __ldcg(&V.v[j]) - gamma;
+                        V.v[j] = vj;
+                        V.u[i] = (double)V.cost[(size_t)i * B.ldc + j] - vj;
+                        V.row4col[j] = i;
+                        V.col4row[i] = j;
+                        V.colbest[j] = 0ull;
+                        if (prev >= 0) { V.col4row[prev] = -1; next[atomicAdd(next_count, 1)] = prev; }
+                        atomicAdd(&B.progress[round & 1], 1);
+                    }
+                }
+                if (!won) next[atomicAdd(next_count, 1)] = i;
+            }
         }
-        __syncthreads();
-        if (lane == 0) { s_w1[warp] = bid.w1; s_w2[warp] = bid.w2; s_j1[warp] = bid.j1; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            PmBid tot = {s_w1[0], s_w2[0], s_j1[0]};
-            for (int w = 1; w < PM_LAP_BID_THREADS / 32; ++w) pm_bid_merge(tot, s_w1[w], s_w2[w], s_j1[w]);
-            // nc == 1: no second best; an unowned single column is simply taken with gamma 0
-            double gamma = (tot.w2 == INFINITY) ? 0.0 : tot.w2 - tot.w1;
-            if (!(gamma > 0.0)) gamma = 0.0;
-            int j1 = tot.j1;
-            if (j1 == INT_MAX || tot.w1 == INFINITY) j1 = -1;                       // all-inf row: phase 2 reports it
-            else if (gamma == 0.0 && V.row4col[j1] >= 0) j1 = -1;                    // zero-increment steal: wait
-            V.bid_col[i] = j1;
-            V.bid_gamma[i] = gamma;
-            if (j1 >= 0) atomicMax(&V.colbest[j1], (unsigned long long)__double_as_longlong(gamma));
-        }
+        grid.sync();
+        // every bid-on column has exactly one winner, which cleared its key above: nothing left to reset
+        if (__ldcg(&B.progress[round & 1]) == 0) { ++round; break; }     // stalled: only zero-increment steals left
     }
-}
-
-__global__ void pm_lap_resolve_kernel(PmLapBatch B, int parity) {
-    const PmLapView V = pm_lap_view(B, blockIdx.y);
-    const int nfree = V.counters[parity];
-    const int32_t *list = parity ? V.free_b : V.free_a;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nfree; idx += gridDim.x * blockDim.x) {
-        const int i = list[idx], j = V.bid_col[i];
-        if (j >= 0 && (unsigned long long)__double_as_longlong(V.bid_gamma[i]) == V.colbest[j]) atomicMin(&V.colwin[j], i);
-    }
-}
-
-// Winners take their column; losers, waiting rows and displaced owners form the next free list.
-__global__ void pm_lap_apply_kernel(PmLapBatch B, int parity) {
-    const PmLapView V = pm_lap_view(B, blockIdx.y);
-    const int nfree = V.counters[parity];
-    const int32_t *list = parity ? V.free_b : V.free_a;
-    int32_t *next = parity ? V.free_a : V.free_b;
-    int32_t *next_count = &V.counters[parity ^ 1];
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nfree; idx += gridDim.x * blockDim.x) {
-        const int i = list[idx], j = V.bid_col[i];
-        if (j >= 0 && V.colwin[j] == i) {
-            const int prev = V.row4col[j];
-            const double vj = V.v[j] - V.bid_gamma[i];
-            V.v[j] = vj;
-            V.u[i] = (double)V.cost[(size_t)i * B.ldc + j] - vj;
-            V.row4col[j] = i;
-            V.col4row[i] = j;
-            if (prev >= 0) { V.col4row[prev] = -1; next[atomicAdd(next_count, 1)] = prev; }
-        } else {
-            next[atomicAdd(next_count, 1)] = i;
-        }
-    }
-}
-
-// Clears the per-column bid slots touched this round, retires the current list, counts the round.
-__global__ void pm_lap_reset_kernel(PmLapBatch B, int parity) {
-    const PmLapView V = pm_lap_view(B, blockIdx.y);
-    const int nfree = V.counters[parity];
-    const int32_t *list = parity ? V.free_b : V.free_a;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nfree; idx += gridDim.x * blockDim.x) {
-        const int j = V.bid_col[list[idx]];
-        if (j >= 0) { V.colbest[j] = 0ull; V.colwin[j] = INT_MAX; }
-    }
-}
-__global__ void pm_lap_round_end_kernel(PmLapBatch B, int parity) {
-    const PmLapView V = pm_lap_view(B, blockIdx.x);
-    if (threadIdx.x == 0) {
-        if (V.counters[parity] > 0) V.counters[2] += 1;
-        V.counters[parity] = 0;   // becomes the "next" list of the following round
-    }
+    if (gtid == 0)
+        for (int b = 0; b < batch; ++b) pm_lap_view(B, b).counters[3] = round;
 }
 
 // ------------------------------------------------------------------------------------- phase 2
@@ -246,8 +263,8 @@ __global__ void __launch_bounds__(PM_LAP_MAX_THREADS, 1) pm_lap_sap_kernel(PmLap
         if (r >= 0) assigned |= 1u << q;
         if (V_IN_REGS) vreg[q] = (c < nc) ? V.v[c] : 0.0;
     }
-    // ordered list of free rows (ascending row index -> deterministic), into free_a
-    int32_t *flist = V.free_a;
+    // ordered list of free rows (ascending row index -> deterministic), into list 0
+    int32_t *flist = V.free_lists;
     if (t == 0) s_nfree = 0;
     __syncthreads();
     for (int base = 0; base < nr; base += nthreads) {
@@ -374,9 +391,9 @@ __global__ void __launch_bounds__(PM_LAP_MAX_THREADS, 1) pm_lap_sap_kernel(PmLap
     tot = pm_block_sum(tot, &s_val[0][0]);
     if (t == 0) {
         V.total[0] = status ? nan("") : tot;
-        V.counters[3] = status;
+        V.counters[4] = status;
         if (V.stats) {
-            V.stats[PM_LAP_STAT_BID_ROUNDS] = V.counters[2];
+            V.stats[PM_LAP_STAT_BID_ROUNDS] = V.counters[3];
             V.stats[PM_LAP_STAT_ROWS_AFTER_BIDDING] = nr - nfree;
             V.stats[PM_LAP_STAT_AUGMENTATIONS] = nfree;
             V.stats[PM_LAP_STAT_DIJKSTRA_STEPS] = steps;
@@ -390,7 +407,7 @@ __global__ void __launch_bounds__(PM_LAP_MAX_THREADS, 1) pm_lap_sap_kernel(PmLap
 extern "C" size_t pm_lap_workspace_bytes(int batch, int nr, int nc) {
     if (batch < 1 || nr < 1 || nc < 1) return 0;
     const int ncp = (nc + 3) & ~3;
-    return (size_t)batch * pm_lap_layout(nr, ncp).per_item;
+    return 256 + (size_t)batch * pm_lap_layout(nr, ncp).per_item;
 }
 
 template <int CPT, bool VR>
@@ -423,22 +440,27 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
     cudaStream_t s = pm_stream(stream);
     PmLapBatch B;
     B.cost = cost; B.cost_stride = (size_t)nr * ldc; B.nr = nr; B.nc = nc; B.ldc = ldc;
-    B.ws = (char *)workspace; B.L = pm_lap_layout(nr, (nc + 3) & ~3);
+    B.ncp = (nc + 3) & ~3;
+    B.L = pm_lap_layout(nr, B.ncp);
+    B.progress = (int32_t *)workspace;
+    B.ws = (char *)workspace + 256;
     B.col4row = col4row; B.stats = (long long *)stats; B.total = total;
 
     pm_lap_init_kernel<<<dim3(32, batch), 256, 0, s>>>(B);
     PM_LAUNCH_CHECK();
-    const int bid_blocks = nr < 1184 ? nr : 1184;                 // 148 SMs x 8 resident CTAs
-    const int flat_blocks = (nr + 255) / 256;
-    for (int r = 0; r < max_bid_rounds; ++r) {
-        const int parity = r & 1;
-        pm_lap_bid_kernel<<<dim3(bid_blocks, batch), PM_LAP_BID_THREADS, 0, s>>>(B, parity);
-        pm_lap_resolve_kernel<<<dim3(flat_blocks, batch), 256, 0, s>>>(B, parity);
-        pm_lap_apply_kernel<<<dim3(flat_blocks, batch), 256, 0, s>>>(B, parity);
-        pm_lap_reset_kernel<<<dim3(flat_blocks, batch), 256, 0, s>>>(B, parity);
-        pm_lap_round_end_kernel<<<batch, 32, 0, s>>>(B, parity);
+    if (max_bid_rounds > 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        PM_CUDA_TRY(cudaGetDevice(&dev));
+        PM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        PM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm_lap_bid_persistent, PM_LAP_BID_THREADS, 0));
+        if (per_sm < 1) { pm_set_error("pm_lap_solve: bidding kernel does not fit on an SM"); return PM_ERR_CUDA; }
+        if (per_sm > 4) per_sm = 4;
+        int grid = sms * per_sm;
+        void *args[] = {(void *)&B, (void *)&batch, (void *)&max_bid_rounds};
+        PM_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)pm_lap_bid_persistent, dim3(grid), dim3(PM_LAP_BID_THREADS),
+                                                args, 0, s));
+        PM_LAUNCH_CHECK();
     }
-    PM_LAUNCH_CHECK_N(5 * max_bid_rounds);
     int rc;
     if (nc <= PM_LAP_CPT * PM_LAP_MAX_THREADS) {
         int threads = ((nc + PM_LAP_CPT - 1) / PM_LAP_CPT + 31) & ~31;

@@ -1,0 +1,97 @@
+"""Host-side logic of the multi-GPU path on CPU: partition arithmetic, and the two exchange steps
+(row all-gather, best-hypothesis reduction) over a world_size-2 gloo group."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from platymatch_b200 import distributed as PD
+
+
+def test_shard_rows_cover_and_align():
+    for n in (1, 127, 128, 7200, 18000, 20000):
+        for world in (1, 2, 4, 8):
+            got, per = [], None
+            for r in range(world):
+                b, e, per = PD.shard_rows(n, r, world)
+                assert (b % 4 == 0 or b == e) and per % 128 == 0 and 0 <= b <= e <= n and e - b <= per
+                got.extend(range(b, e))
+            assert got == list(range(n))
+
+
+def test_pair_and_hypothesis_partitions():
+    pairs = PD.all_pairs(12)
+    assert len(pairs) == 66 and pairs[0] == (0, 1) and pairs[-1] == (10, 11)
+    for world in (1, 2, 4, 8):
+        seen = []
+        for r in range(world):
+            mine = PD.pairs_for_rank(12, r, world)
+            assert abs(len(mine) - 66 / world) < 1
+            seen += mine
+        assert sorted(seen) == pairs
+        hyp = sorted(q for r in range(world) for q in PD.hypotheses_for_rank(4, r, world))
+        assert hyp == [0, 1, 2, 3]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # --- row all-gather: every rank fills its shard of a known matrix
+        n_rows, ld = 300, 8
+        truth = torch.arange(n_rows * ld, dtype=torch.float32).reshape(n_rows, ld)
+        b, e, per = PD.shard_rows(n_rows, rank, world)
+        local = torch.zeros((per, ld), dtype=torch.float32)
+        local[: e - b] = truth[b:e]
+        full = PD.allgather_rows(local, n_rows, per)
+        ok_rows = bool(torch.equal(full, truth))
+        # --- best-hypothesis reduction: ties resolve to the first hypothesis (np.argmax)
+        inl_all = [17, 42, 42, 5]
+        mine = PD.hypotheses_for_rank(4, rank, world)
+        inl = [torch.tensor(inl_all[h], dtype=torch.int32) for h in mine]
+        mats = torch.stack([torch.full((16,), float(h), dtype=torch.float64) for h in mine])
+        inliers, transforms, best = PD.reduce_best_hypothesis(inl, mats, mine, 4)
+        ok_best = best == 1 and inliers.tolist() == inl_all and all(float(transforms[h, 0]) == h for h in range(4))
+        # --- result gather
+        pairs = PD.all_pairs(5)
+        local_res = {k: np.full((4, 4), float(k)) for k in range(len(pairs)) if k % world == rank}
+        out = PD.gather_results(local_res, len(pairs), None)
+        ok_gather = all(float(out[k, 0]) == k for k in range(len(pairs)))
+        q.put((rank, ok_rows, ok_best, ok_gather))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_steps_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok_rows, ok_best, ok_gather in results:
+        assert ok_rows and ok_best and ok_gather, (rank, ok_rows, ok_best, ok_gather)
+
+
+def test_single_process_degenerates():
+    local = torch.ones((128, 4))
+    assert PD.allgather_rows(local, 100, 128).shape == (100, 4)
+    inl, tr, best = PD.reduce_best_hypothesis([torch.tensor(3), torch.tensor(9)], torch.zeros((2, 16), dtype=torch.float64),
+                                              [0, 1], 2)
+    assert best == 1 and inl.tolist() == [3, 9]

@@ -246,10 +246,13 @@ def test_ransac_per_trial_counts_and_device_rng(O, D, torch):
     a1, i1, _, _ = D.ransac_affine(md, fd, 500, 16.0, 4, None, seed=123)
     a2, i2, _, _ = D.ransac_affine(md, fd, 500, 16.0, 4, None, seed=123)
     assert i1.item() == i2.item() and torch.equal(a1, a2) and i1.item() > 0.9 * k
-    # no inliers at all -> all-ones matrix and 0, as the reference (shape_context.py:120)
-    far = torch.from_numpy(np.random.default_rng(0).normal(size=(50, 3)) * 1e6).cuda()
-    a0, i0, t0, _ = D.ransac_affine(md[:50].contiguous(), far, 20, 1e-3, 4, None, seed=1)
-    assert i0.item() == 0 and torch.all(a0 == 1.0)
+    # no inliers at all (negative threshold) -> all-ones matrix and 0, as the reference (shape_context.py:120)
+    a0, i0, t0, _ = D.ransac_affine(md, fd, 20, -1.0, 4, None, seed=1)
+    assert i0.item() == 0 and torch.all(a0 == 1.0) and t0.item() == -1
+    # coplanar (degenerate) samples never win with NaNs
+    flat = md.clone(); flat[:, 2] = 5.0
+    a3, i3, _, _ = D.ransac_affine(flat, fd, 50, 16.0, 4, None, seed=2)
+    assert i3.item() == 0 and torch.all(torch.isfinite(a3))
 
 
 # ------------------------------------------------------------------------------ K6 + small ops
