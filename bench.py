@@ -197,7 +197,7 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = load()
-    bid_rounds = args.bid_rounds if args.bid_rounds is not None else 128
+    bid_rounds = args.bid_rounds if args.bid_rounds is not None else 2048
     kw = dict(ransac_trials=args.trials, icp_iterations=ICP_ITERS, max_bid_rounds=bid_rounds)
 
     # distinct specimen pairs per rank and per step slot (4 slots cycled)

@@ -25,7 +25,7 @@
 
 namespace cg = cooperative_groups;
 
-#define PM_LAP_BID_THREADS 256
+#define PM_LAP_BID_THREADS 1024
 #define PM_LAP_CPT 8
 #define PM_LAP_MAX_THREADS 1024
 
@@ -148,14 +148,30 @@ __global__ void __launch_bounds__(PM_LAP_BID_THREADS) pm_lap_bid_persistent(PmLa
                 const int i = __ldcg(&list[idx]);
                 const float *ci = V.cost + (size_t)i * B.ldc;
                 PmBid bid = {INFINITY, INFINITY, INT_MAX};
-                for (int j = threadIdx.x * 4; j < B.nc; j += PM_LAP_BID_THREADS * 4) {
-                    const float4 c4 = *reinterpret_cast<const float4 *>(ci + j);   // ldc % 4 == 0, pad readable
-                    const double2 va = __ldcg(reinterpret_cast<const double2 *>(V.v + j));
-                    const double2 vb = __ldcg(reinterpret_cast<const double2 *>(V.v + j + 2));
-                    if (j + 0 < B.nc) pm_bid_push(bid, (double)c4.x - va.x, j + 0);
-                    if (j + 1 < B.nc) pm_bid_push(bid, (double)c4.y - va.y, j + 1);
-                    if (j + 2 < B.nc) pm_bid_push(bid, (double)c4.z - vb.x, j + 2);
-                    if (j + 3 < B.nc) pm_bid_push(bid, (double)c4.w - vb.y, j + 3);
+                // two float4 sweeps per trip so that all loads of a thread are in flight together
+                for (int j0 = threadIdx.x * 4; j0 < B.nc; j0 += PM_LAP_BID_THREADS * 8) {
+                    const int j1 = j0 + PM_LAP_BID_THREADS * 4;
+                    const bool second = j1 < B.nc;
+                    const float4 c4 = *reinterpret_cast<const float4 *>(ci + j0);   // ldc % 4 == 0, pad readable
+                    const double2 va = __ldcg(reinterpret_cast<const double2 *>(V.v + j0));
+                    const double2 vb = __ldcg(reinterpret_cast<const double2 *>(V.v + j0 + 2));
+                    float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    double2 wa = make_double2(0.0, 0.0), wb = make_double2(0.0, 0.0);
+                    if (second) {
+                        d4 = *reinterpret_cast<const float4 *>(ci + j1);
+                        wa = __ldcg(reinterpret_cast<const double2 *>(V.v + j1));
+                        wb = __ldcg(reinterpret_cast<const double2 *>(V.v + j1 + 2));
+                    }
+                    if (j0 + 0 < B.nc) pm_bid_push(bid, (double)c4.x - va.x, j0 + 0);
+                    if (j0 + 1 < B.nc) pm_bid_push(bid, (double)c4.y - va.y, j0 + 1);
+                    if (j0 + 2 < B.nc) pm_bid_push(bid, (double)c4.z - vb.x, j0 + 2);
+                    if (j0 + 3 < B.nc) pm_bid_push(bid, (double)c4.w - vb.y, j0 + 3);
+                    if (second) {
+                        if (j1 + 0 < B.nc) pm_bid_push(bid, (double)d4.x - wa.x, j1 + 0);
+                        if (j1 + 1 < B.nc) pm_bid_push(bid, (double)d4.y - wa.y, j1 + 1);
+                        if (j1 + 2 < B.nc) pm_bid_push(bid, (double)d4.z - wb.x, j1 + 2);
+                        if (j1 + 3 < B.nc) pm_bid_push(bid, (double)d4.w - wb.y, j1 + 3);
+                    }
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -454,7 +470,7 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
         PM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         PM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm_lap_bid_persistent, PM_LAP_BID_THREADS, 0));
         if (per_sm < 1) { pm_set_error("pm_lap_solve: bidding kernel does not fit on an SM"); return PM_ERR_CUDA; }
-        if (per_sm > 4) per_sm = 4;
+        if (per_sm > 1) per_sm = 1;          // one CTA per SM: the grid barrier scales with the CTA count
         int grid = sms * per_sm;
         void *args[] = {(void *)&B, (void *)&batch, (void *)&max_bid_rounds};
         PM_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)pm_lap_bid_persistent, dim3(grid), dim3(PM_LAP_BID_THREADS),

@@ -91,7 +91,7 @@ def chi2_cost(a_t, n1, b_t, n2, out=None, row_begin=0, row_end=None):
     return out
 
 
-def lap_solve(cost, nr, nc, max_bid_rounds=128):
+def lap_solve(cost, nr, nc, max_bid_rounds=2048):
     """cost [batch, nr, ldc] float32 (nr <= nc) -> col4row [batch, nr] int32, total [batch] f64, stats [batch, 8] i64."""
     torch = _torch()
     if cost.dim() == 2:

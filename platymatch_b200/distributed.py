@@ -122,7 +122,7 @@ def gather_results(local, n_total, owner_of, group=None):
 
 # ----------------------------------------------------------------------------- CUDA paths
 def register_pair_sharded(moving, fixed, *, ransac_samples=4, ransac_trials=8000, ransac_error=16, icp_iterations=50,
-                          seed=0, hypotheses=None, max_bid_rounds=128, shard_rows_of_cost=True, group=None):
+                          seed=0, hypotheses=None, max_bid_rounds=2048, shard_rows_of_cost=True, group=None):
     """One registration spread over all ranks (configs 2/4 at N > 1): cost-matrix rows of every hypothesis are
     computed in row shards and all-gathered to all ranks; hypothesis q's LAP + RANSAC run on rank q % world;
     (inliers, A) are all-gathered; every rank runs the (deterministic) ICP.  Returns the same dict on every rank."""

@@ -7,7 +7,7 @@ from . import device as D
 __all__ = ["linear_sum_assignment"]
 
 
-def linear_sum_assignment(cost_matrix, maximize=False, return_stats=False, max_bid_rounds=128):
+def linear_sum_assignment(cost_matrix, maximize=False, return_stats=False, max_bid_rounds=2048):
     """Minimum-cost assignment of a dense (nr, nc) matrix -> (row_ind, col_ind) int64 arrays.
 
     The matrix is solved as float32 values with float64 duals (optimal for the float32-rounded

@@ -60,7 +60,7 @@ def _draw_or_take(sample_indices, q):
 
 
 def register_described(dm, df, ransac_samples=4, ransac_trials=8000, ransac_error=16, icp_iterations=50,
-                       hypotheses=None, seed=0, sample_indices=None, max_bid_rounds=128, cost_out=None,
+                       hypotheses=None, seed=0, sample_indices=None, max_bid_rounds=2048, cost_out=None,
                        keep_cost=False, stage_hook=None):
     """Cost matrices -> LAP -> RANSAC -> argmax -> ICP for two described clouds (device resident).
 
@@ -136,7 +136,7 @@ def _to_host(res):
 
 def estimate_transform_unsupervised(moving, fixed, *, ransac_samples=4, ransac_trials=8000, ransac_error=16,
                                     icp_iterations=50, transform='Affine', seed=0, sample_indices=None,
-                                    as_reference=False, hypotheses=None, max_bid_rounds=128, keep_cost=False):
+                                    as_reference=False, hypotheses=None, max_bid_rounds=2048, keep_cost=False):
     """Unsupervised registration of two nuclei clouds (reference _dock_widget.py:526-721, widget defaults).
 
     moving, fixed: 3xN (or 4xN) float64 arrays, zyx.  Returns a dict of numpy results:
