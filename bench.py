@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--bid-rounds", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stages", action="store_true", help="print a per-stage device-time breakdown to stderr")
+    ap.add_argument("--lean", action="store_true",
+                    help="profiling aid: warm-up + timed resident steps only (no e2e, stage, roofline or CPU legs)")
     return ap.parse_args()
 
 
@@ -257,6 +259,12 @@ def run_b200(args):
     ms = timed(step_resident, args.steps)
     launches = lib.pm_launch_count() - l0
     clocks = sampler.stop() if sampler else None
+    if args.lean:
+        if rank == 0:
+            print(json.dumps({"lean": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches)}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     for s in range(min(args.warmup, 2)):
         step_e2e(s)
     ms_e2e = timed(step_e2e, args.steps)
