@@ -83,22 +83,30 @@ int pm_shape_context_hist(const double *pts, int n, const double *centroid, cons
                           const double *mean_dist, const double *r_edges, int n_redges, int n_variants,
                           uint32_t *counts, uint32_t *dropped, unsigned long long *edge_ties, void *stream);
 
-/* Normalise integer histograms (shape_context.py:41) to float32 for the cost kernel, written
- * bin-major ("transposed"): out[k * ld + i] = counts[i][k] / rowsum_i, ld >= n (pad columns are
- * zero-filled up to ld).  zero_sentinel replaces exact zeros (0 keeps them; the chi2 kernel wants
- * its B operand with PM_CHI2_ZERO_SENTINEL so that 0/0 bins contribute 0 without a branch). */
-#define PM_CHI2_ZERO_SENTINEL 1e-30f
+/* Normalise integer histograms (shape_context.py:41) to float32, written bin-major ("transposed"):
+ * out[k * ld + i] = counts[i][k] / rowsum_i, ld >= n (pad columns hold zero_sentinel), exact zeros
+ * replaced by zero_sentinel (0 keeps them).  Generic helper; the cost kernel uses pm_chi2_operand. */
 int pm_normalise_hist(const uint32_t *counts, int n, float *out, int ld, float zero_sentinel, void *stream);
 
 /* ---- K3  chi^2 histogram-distance cost matrix ---------------------------------------------------
  * get_unary_distance (shape_context.py:88-99) over all pairs (_dock_widget.py:547-602):
- * cost[i][j] = 0.5 * sum_k (a_ik - b_jk)^2 / (a_ik + b_jk), equal bins skipped.  FP32, register tiled.
- *   a_t  [360][lda] float32 bin-major histograms of the ROW cloud (exact zeros)
- *   b_t  [360][ldb] float32 bin-major histograms of the COLUMN cloud (zeros = PM_CHI2_ZERO_SENTINEL)
- *   rows [row_begin,row_end) of the n1 x n2 matrix are written to cost + (i - row_begin) * ldc
- * (row sharding across GPUs: each rank passes its own range and buffer). */
-int pm_chi2_cost(const float *a_t, int lda, int n1, const float *b_t, int ldb, int n2, int row_begin,
-                 int row_end, float *cost, int ldc, void *stream);
+ * cost[i][j] = 0.5 * sum_k (a_ik - b_jk)^2 / (a_ik + b_jk), equal bins skipped.  Packed FP32,
+ * register tiled, two bins per reciprocal, structurally empty bins skipped per 128 x 128 tile.
+ *
+ * pm_chi2_operand prepares one cloud's histograms for either side of the matrix:
+ *   out   [361][ld] float32 bin-major, ld = n rounded up to 128: count / row total (one rounding);
+ *         empty bins, pad columns and the extra "null bin" row 360 hold PM_CHI2_EPS (2^-60), which
+ *         makes equal-and-empty bins contribute exactly 0 without a branch
+ *   mask  [ld/128][12] uint32: bit k of block q = some histogram in rows [128q, 128q+128) has a
+ *         non-empty bin k
+ * pm_chi2_cost writes rows [row_begin,row_end) of the n1 x n2 matrix to cost + (i - row_begin) * ldc
+ * (row sharding across GPUs: each rank passes its own 128-aligned range and buffer). */
+#define PM_CHI2_EPS 8.673617379884035e-19f
+int pm_chi2_operand(const uint32_t *counts, int n, float *out, int ld, uint32_t *mask, void *stream);
+/* same from already-normalised float32 histograms [n][360] (values <= 0 count as empty) */
+int pm_chi2_operand_f32(const float *hist, int n, float *out, int ld, uint32_t *mask, void *stream);
+int pm_chi2_cost(const float *a_t, int lda, const uint32_t *a_mask, int n1, const float *b_t, int ldb,
+                 const uint32_t *b_mask, int n2, int row_begin, int row_end, float *cost, int ldc, void *stream);
 
 /* ---- K4  linear sum assignment ------------------------------------------------------------------
  * Replaces scipy.optimize.linear_sum_assignment at _dock_widget.py:604-611 for nr <= nc

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libplatymatch_b200.so")
 
 NBINS = 360
 LAP_STATS = 8
-CHI2_ZERO_SENTINEL = 1e-30
+CHI2_EPS = 2.0 ** -60
 CHI2_TILE = 128
 
 _vp, _i, _d, _sz, _u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t, ctypes.c_ulonglong
@@ -29,7 +29,9 @@ SIGNATURES = {
     "pm_mean_distance": (_i, [_vp, _i, _vp, _vp, _sz, _vp]),
     "pm_shape_context_hist": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "pm_normalise_hist": (_i, [_vp, _i, _vp, _i, ctypes.c_float, _vp]),
-    "pm_chi2_cost": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "pm_chi2_operand": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+    "pm_chi2_operand_f32": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+    "pm_chi2_cost": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp]),
     "pm_lap_workspace_bytes": (_sz, [_i, _i, _i]),
     "pm_lap_solve": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pm_ransac_workspace_bytes": (_sz, [_i]),

@@ -68,7 +68,7 @@ def padded(n, tile=CHI2_TILE):
 
 
 def normalise(counts_2d, zero_sentinel=0.0):
-    """[N,360] counts -> bin-major float32 [360, ld] (ld = N rounded up to the chi2 tile)."""
+    """[N,360] counts -> bin-major float32 [360, ld] (ld = N rounded up to 128); generic helper."""
     torch = _torch()
     n = counts_2d.shape[0]
     ld = padded(n)
@@ -78,16 +78,41 @@ def normalise(counts_2d, zero_sentinel=0.0):
     return out
 
 
-def chi2_cost(a_t, n1, b_t, n2, out=None, row_begin=0, row_end=None):
-    """cost[row_begin:row_end, :n2] float32 (ld = n2 rounded up to 4); a_t exact zeros, b_t sentinel zeros."""
+class Chi2Operand:
+    """One side of the chi^2 cost kernel: bin-major float32 histograms [361, ld] (empty bins = 2^-60, row
+    360 = null bin) and the per-128-block non-empty-bin masks [ld/128, 12] (see pm_chi2_operand)."""
+
+    def __init__(self, t, mask, n):
+        self.t, self.mask, self.n, self.ld = t, mask, n, t.shape[1]
+
+
+def chi2_operand(hist_2d):
+    """[N,360] integer counts (int32/uint32: normalised by the row total) or float32 histograms -> Chi2Operand."""
     torch = _torch()
+    n = hist_2d.shape[0]
+    ld = padded(n)
+    out = torch.empty((NBINS + 1, ld), dtype=torch.float32, device=hist_2d.device)
+    mask = torch.empty((ld // CHI2_TILE, 12), dtype=torch.int32, device=hist_2d.device)
+    hist_2d = hist_2d.contiguous()
+    if hist_2d.dtype == torch.float32:
+        check(load().pm_chi2_operand_f32(ptr(hist_2d), n, ptr(out), ld, ptr(mask), stream_ptr()), "pm_chi2_operand_f32")
+    else:
+        assert hist_2d.dtype in (torch.int32, torch.uint32)
+        check(load().pm_chi2_operand(ptr(hist_2d), n, ptr(out), ld, ptr(mask), stream_ptr()), "pm_chi2_operand")
+    return Chi2Operand(out, mask, n)
+
+
+def chi2_cost(a, b, out=None, row_begin=0, row_end=None):
+    """cost[row_begin:row_end, :b.n] float32 (ld = b.n rounded up to 4) for two Chi2Operands (rows a, columns b)."""
+    torch = _torch()
+    n1, n2 = a.n, b.n
     row_end = n1 if row_end is None else row_end
     ldc = (n2 + 3) // 4 * 4
     if out is None:
-        out = torch.empty((row_end - row_begin, ldc), dtype=torch.float32, device=a_t.device)
+        out = torch.empty((row_end - row_begin, ldc), dtype=torch.float32, device=a.t.device)
     assert out.stride(-1) == 1 and out.shape[-1] >= n2
-    check(load().pm_chi2_cost(ptr(a_t), a_t.shape[1], n1, ptr(b_t), b_t.shape[1], n2, row_begin, row_end, ptr(out),
-                              out.stride(-2), stream_ptr()), "pm_chi2_cost")
+    check(load().pm_chi2_cost(ptr(a.t), a.ld, ptr(a.mask), n1, ptr(b.t), b.ld, ptr(b.mask), n2, row_begin, row_end,
+                              ptr(out), out.stride(-2), stream_ptr()), "pm_chi2_cost")
     return out
 
 

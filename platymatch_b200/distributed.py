@@ -144,12 +144,12 @@ def register_pair_sharded(moving, fixed, *, ransac_samples=4, ransac_trials=8000
         if world > 1 and shard_rows_of_cost:
             local = torch.zeros((per, ldc), dtype=torch.float32, device=dm.pts.device)
             if end > begin:
-                D.chi2_cost(dm.operand(a, False), n1, df.operand(b, True), n2, out=local, row_begin=begin, row_end=end)
+                D.chi2_cost(dm.operand(a), df.operand(b), out=local, row_begin=begin, row_end=end)
             full = allgather_rows(local, n1, per, group)
             if q in mine:
                 costs[q] = full.contiguous()
         elif q in mine:
-            costs[q] = D.chi2_cost(dm.operand(a, False), n1, df.operand(b, True), n2)
+            costs[q] = D.chi2_cost(dm.operand(a), df.operand(b))
     inl_local, a_local, lap_cost = [], [], {}
     rows = torch.arange(n1, dtype=torch.int32, device=dm.pts.device)
     for q in mine:

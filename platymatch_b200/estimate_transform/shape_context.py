@@ -6,7 +6,6 @@ conventions (numpy float64 in and out); the work runs on the GPU through the C A
 import numpy as np
 
 from .. import device as D
-from .._lib import CHI2_ZERO_SENTINEL
 
 __all__ = ["get_unary", "get_unary_counts", "get_unary_distance", "unary_distance_matrix", "do_ransac"]
 
@@ -42,26 +41,18 @@ def get_unary(centroid, mean_distance, detections, type, transposed=False):
     return tuple(out)
 
 
-def _hist_to_device(sc, zero_sentinel):
-    """(N,360) normalised float64 histograms -> bin-major float32 [360, ld] on the GPU."""
+def _hist_to_device(sc):
+    """(N,360) normalised float64 histograms -> chi^2 operand on the GPU (float32 arithmetic)."""
     torch = D._torch()
-    sc = np.asarray(sc, dtype=np.float64)
-    n = sc.shape[0]
-    ld = D.padded(n)
-    a = np.full((sc.shape[1], ld), zero_sentinel, dtype=np.float32)
-    a[:, :n] = sc.T.astype(np.float32)
-    if zero_sentinel:
-        a[a == 0] = zero_sentinel
-    return torch.from_numpy(a).cuda()
+    sc = np.ascontiguousarray(np.asarray(sc, dtype=np.float64).astype(np.float32))
+    return D.chi2_operand(torch.from_numpy(sc).cuda())
 
 
 def unary_distance_matrix(sc_a, sc_b):
     """The double loops of reference _dock_widget.py:556-602 as one call: U[i,j] =
     get_unary_distance(sc_a[i], sc_b[j]); float32 arithmetic on the GPU, returned as float64."""
     sc_a, sc_b = np.atleast_2d(sc_a), np.atleast_2d(sc_b)
-    a_t = _hist_to_device(sc_a, 0.0)
-    b_t = _hist_to_device(sc_b, CHI2_ZERO_SENTINEL)
-    cost = D.chi2_cost(a_t, sc_a.shape[0], b_t, sc_b.shape[0])
+    cost = D.chi2_cost(_hist_to_device(sc_a), _hist_to_device(sc_b))
     return cost[:, :sc_b.shape[0]].cpu().numpy().astype(np.float64)
 
 

@@ -8,7 +8,6 @@ results stays on the GPU; stage boundaries are stream-ordered kernel launches th
 import numpy as np
 
 from . import device as D
-from ._lib import CHI2_ZERO_SENTINEL
 
 __all__ = ["HYPOTHESES_REFERENCE", "HYPOTHESES_DISTINCT", "estimate_transform_unsupervised",
            "estimate_transform_supervised", "Descriptors", "describe_cloud", "register_described"]
@@ -29,12 +28,11 @@ class Descriptors:
         self.n = pts.shape[0]
         self._ops = {}
 
-    def operand(self, variant, as_columns):
-        """bin-major float32 histogram of `variant` (1-based); column operands carry the zero sentinel."""
-        key = (variant, bool(as_columns))
-        if key not in self._ops:
-            self._ops[key] = D.normalise(self.counts[variant - 1], CHI2_ZERO_SENTINEL if as_columns else 0.0)
-        return self._ops[key]
+    def operand(self, variant):
+        """chi^2 operand (bin-major float32 histograms + block masks) of `variant` (1-based); either side."""
+        if variant not in self._ops:
+            self._ops[variant] = D.chi2_operand(self.counts[variant - 1])
+        return self._ops[variant]
 
 
 def describe_cloud(cloud, n_variants, transposed=False):
@@ -77,9 +75,9 @@ def register_described(dm, df, ransac_samples=4, ransac_trials=8000, ransac_erro
     cost = cost_out if cost_out is not None else torch.empty((H, nr, ldc), dtype=torch.float32, device=dm.pts.device)
     for q, (a, b) in enumerate(hyps):
         if swap:
-            D.chi2_cost(df.operand(b, False), n2, dm.operand(a, True), n1, out=cost[q])
+            D.chi2_cost(df.operand(b), dm.operand(a), out=cost[q])
         else:
-            D.chi2_cost(dm.operand(a, False), n1, df.operand(b, True), n2, out=cost[q])
+            D.chi2_cost(dm.operand(a), df.operand(b), out=cost[q])
     if stage_hook: stage_hook("chi2_cost")
     col4row, lap_total, lap_stats = D.lap_solve(cost, nr, nc, max_bid_rounds)
     if stage_hook: stage_hook("lap")

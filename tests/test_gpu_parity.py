@@ -154,6 +154,44 @@ def test_chi2_vs_oracle_shapes(O, torch, n1, n2):
     assert get_unary_distance(a[0], a[0]) == 0.0
 
 
+@pytest.mark.parametrize("case", ["disjoint", "one_shared", "odd_shared", "blocks_differ", "dense", "row_only_extra"])
+def test_chi2_structured_sparsity(O, torch, case):
+    """The kernel skips bins that are empty for a whole 128-block on both sides and folds one-sided bins
+    into row / column sums: exercise every list shape (no shared bin, odd counts, per-block differences)."""
+    from platymatch_b200.estimate_transform.shape_context import unary_distance_matrix
+    rng = np.random.default_rng(len(case))
+    n1, n2 = 300, 391
+
+    def hist(n, bins_of_block):
+        c = np.zeros((n, 360))
+        for blk in range((n + 127) // 128):
+            rows = slice(blk * 128, min(n, blk * 128 + 128))
+            bins = np.asarray(bins_of_block(blk))
+            m = rows.stop - rows.start
+            vals = rng.integers(0, 5, size=(m, len(bins))).astype(np.float64)
+            vals[np.arange(m), rng.integers(0, len(bins), size=m)] += 1       # no empty histogram
+            c[rows][:, bins] = vals
+        return c / c.sum(1, keepdims=True)
+
+    if case == "disjoint":
+        a, b = hist(n1, lambda q: np.arange(0, 40)), hist(n2, lambda q: np.arange(100, 171))
+    elif case == "one_shared":
+        a, b = hist(n1, lambda q: np.arange(0, 40)), hist(n2, lambda q: np.arange(39, 90))
+    elif case == "odd_shared":
+        a, b = hist(n1, lambda q: np.arange(5, 76)), hist(n2, lambda q: np.arange(31, 64))          # 33 shared
+    elif case == "blocks_differ":
+        a = hist(n1, lambda q: np.arange(q * 50, q * 50 + 97))
+        b = hist(n2, lambda q: np.arange(300 - q * 70, 360 - q * 70 + (q % 2)))
+    elif case == "dense":
+        a, b = hist(n1, lambda q: np.arange(360)), hist(n2, lambda q: np.arange(360))
+    else:
+        a, b = hist(n1, lambda q: np.arange(0, 359)), hist(n2, lambda q: np.arange(8, 24))
+    U, ref = unary_distance_matrix(a, b), O.unary_distance_matrix(a, b)
+    assert np.allclose(U, ref, rtol=1e-5, atol=0), float(np.abs(U / ref - 1).max())
+    V = unary_distance_matrix(a, a)
+    assert np.all(np.diag(V) == 0.0) and np.allclose(V, O.unary_distance_matrix(a, a), rtol=1e-5, atol=0)
+
+
 # ------------------------------------------------------------------------------ K4
 def _check_lap(O, cost, **kw):
     from platymatch_b200.lap import linear_sum_assignment
