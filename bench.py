@@ -356,7 +356,10 @@ def run_b200(args):
                              "frac": chi2_bytes / (chi2_ms * 1e-3) / 1e9 / hbm_peak, "of": "measured"}},
         "stages_ms": stage_ms,
         "lap_stats": {"bid_rounds": [s[0] for s in lap_stats], "rows_after_bidding": [s[1] for s in lap_stats],
-                      "augmentations": [s[2] for s in lap_stats], "dijkstra_steps": [s[3] for s in lap_stats]},
+                      "augmentations": [s[2] for s in lap_stats], "dijkstra_steps": [s[3] for s in lap_stats],
+                      "bids": [s[5] for s in lap_stats], "refreshes": [s[6] for s in lap_stats],
+                      "retries": [s[7] for s in lap_stats], "parked": [s[8] for s in lap_stats],
+                      "refresh_cycles": [s[9] for s in lap_stats], "auction_cycles": [s[10] for s in lap_stats]},
     }
     if not args.no_cpu_baseline:
         cb = cpu_sample(pairs[0], args.trials, ICP_ITERS)

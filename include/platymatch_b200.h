@@ -110,23 +110,37 @@ int pm_chi2_cost(const float *a_t, int lda, const uint32_t *a_mask, int n1, cons
 
 /* ---- K4  linear sum assignment ------------------------------------------------------------------
  * Replaces scipy.optimize.linear_sum_assignment at _dock_widget.py:604-611 for nr <= nc
- * (the host mirror transposes otherwise, as scipy does).  Exact: dual-feasible parallel bidding
- * (epsilon = 0, keeps complementary slackness exactly) followed by shortest augmenting paths with
- * float64 duals — optimal for the float32 matrix given.
+ * (the host mirror transposes otherwise, as scipy does).  Exact, two phases: an epsilon = 0 auction
+ * (keeps complementary slackness exactly) followed by shortest augmenting paths with float64 duals
+ * for the rows the auction parks — optimal for the float32 matrix given.
+ *   algorithm  PM_LAP_ALGO_AUTO picks the sparse asynchronous auction (certified candidate lists,
+ *              prices in shared memory) whenever the column prices fit in shared memory, else the
+ *              dense grid-wide auction; max_bid_rounds = 0 skips the auction (pure augmenting paths);
+ *              for the sparse auction a "round" is a budget of one bid per row
  *   cost     [batch][nr][ldc] float32, ldc >= nc
  *   col4row  [batch][nr] int32 out (column assigned to each row; rows are implicitly 0..nr-1)
  *   total    [batch] float64 out: sum of assigned costs
  *   stats    [batch][PM_LAP_STATS] int64 out, may be NULL (see PM_LAP_STAT_*)
  * workspace: pm_lap_workspace_bytes(batch, nr, nc). */
-#define PM_LAP_STATS 8
-#define PM_LAP_STAT_BID_ROUNDS 0
+#define PM_LAP_STATS 12
+#define PM_LAP_STAT_BID_ROUNDS 0 /* dense: rounds run; sparse: largest number of bids made by one warp */
 #define PM_LAP_STAT_ROWS_AFTER_BIDDING 1
 #define PM_LAP_STAT_AUGMENTATIONS 2
 #define PM_LAP_STAT_DIJKSTRA_STEPS 3
 #define PM_LAP_STAT_STATUS 4 /* 0 ok, -4 infeasible */
+#define PM_LAP_STAT_BIDS 5      /* sparse auction: bids committed or parked */
+#define PM_LAP_STAT_REFRESHES 6 /* sparse auction: candidate lists rebuilt from the dense row */
+#define PM_LAP_STAT_RETRIES 7   /* sparse auction: bids recomputed because the price moved */
+#define PM_LAP_STAT_PARKED 8          /* sparse auction: rows parked for phase 2 (zero-increment steals) */
+#define PM_LAP_STAT_REFRESH_CYCLES 9  /* sparse auction: SM cycles spent rebuilding lists, summed over warps */
+#define PM_LAP_STAT_AUCTION_CYCLES 10 /* sparse auction: SM cycles of the longest-running warp */
+#define PM_LAP_ALGO_AUTO 0
+#define PM_LAP_ALGO_SPARSE_AUCTION 1
+#define PM_LAP_ALGO_DENSE_AUCTION 2
 size_t pm_lap_workspace_bytes(int batch, int nr, int nc);
-int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ldc, int max_bid_rounds, int32_t *col4row,
-                 double *total, int64_t *stats, void *workspace, size_t workspace_bytes, void *stream);
+int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ldc, int max_bid_rounds, int algorithm,
+                 int32_t *col4row, double *total, int64_t *stats, void *workspace, size_t workspace_bytes,
+                 void *stream);
 
 /* ---- K5  affine RANSAC ---------------------------------------------------------------------------
  * do_ransac (shape_context.py:103-139) with get_affine_transform (find_transform.py:4-17) on the

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libplatymatch_b200.so")
 
 NBINS = 360
-LAP_STATS = 8
+LAP_STATS = 12
 CHI2_EPS = 2.0 ** -60
 CHI2_TILE = 128
 
@@ -33,7 +33,7 @@ SIGNATURES = {
     "pm_chi2_operand_f32": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "pm_chi2_cost": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp]),
     "pm_lap_workspace_bytes": (_sz, [_i, _i, _i]),
-    "pm_lap_solve": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pm_lap_solve": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pm_ransac_workspace_bytes": (_sz, [_i]),
     "pm_ransac_affine": (_i, [_vp, _vp, _i, _vp, _i, _i, _d, _u64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pm_icp_workspace_bytes": (_sz, [_i]),

@@ -5,7 +5,11 @@
 // Same optimum (equal total cost; identical assignment where the optimum is unique), different
 // schedule, built for the GPU:
 //
-//  Phase 1 — parallel bidding with epsilon = 0 (all SMs).  Every free row scans its cost row against
+//  Phase 1 (default, "sparse asynchronous auction") — see the block comment above pm_ls_auction_kernel:
+//    epsilon = 0 bidding over certified per-row candidate lists, 32 independent warps per matrix,
+//    prices in shared memory, no barriers.
+//  Phase 1 (fallback for column counts whose prices do not fit in shared memory, algorithm = 2) —
+//    parallel bidding with epsilon = 0 (all SMs).  Every free row scans its cost row against
 //    the column prices v and bids for its best column j1 with increment gamma = w2 - w1 (second best
 //    minus best reduced value).  Per column the largest increment wins (ties: lowest row), the price
 //    drops by gamma and the previous owner is released.  With epsilon = 0 every assigned edge stays
@@ -39,15 +43,28 @@ struct PmLapView {
     unsigned long long *colbest;  // [nc] winning bid key of the round (0 = no bid)
     int32_t *free_lists;    // [3][nr] rotating free-row lists
     int32_t *counters;      // [0..2] list counts, [3] bid rounds run, [4] status
+    int32_t *lcol;          // [nr][PM_LS_K] candidate columns (-1 = empty slot)
+    float *lcost;           // [nr][PM_LS_K] their costs
+    double *tau;            // [nr] every column outside the list has c - v >= tau, forever
+    double *width;          // [nr] value range the list covered when it was built (refresh window)
+    unsigned short *ring;   // [ring_cap] ticket ring of displaced rows when it does not fit in shared memory
     long long *stats;       // [PM_LAP_STATS] or null
     double *total;
 };
 
 static inline size_t pm_lap_align(size_t x) { return (x + 255) & ~(size_t)255; }
 
+#define PM_LS_K 128          // candidate-list slots per row: 32 lanes x 4
+
 struct PmLapLayout {
-    size_t u, v, row4col, bid_col, bid_gamma, colbest, free_lists, counters, per_item;
+    size_t u, v, row4col, bid_col, bid_gamma, colbest, free_lists, counters, lcol, lcost, tau, width, ring, per_item;
 };
+
+static unsigned pm_ls_ring_cap(int nr) {   // power of two >= nr: the ring can hold every row at once
+    unsigned c = 1;
+    while (c < (unsigned)nr) c <<= 1;
+    return c;
+}
 
 static PmLapLayout pm_lap_layout(int nr, int nc) {
     PmLapLayout L;
@@ -60,6 +77,11 @@ static PmLapLayout pm_lap_layout(int nr, int nc) {
     L.colbest = o; o += pm_lap_align((size_t)nc * 8);
     L.free_lists = o; o += pm_lap_align((size_t)nr * 4 * 3);
     L.counters = o; o += pm_lap_align(16 * 4);
+    L.lcol = o; o += pm_lap_align((size_t)nr * PM_LS_K * 4);
+    L.lcost = o; o += pm_lap_align((size_t)nr * PM_LS_K * 4);
+    L.tau = o; o += pm_lap_align((size_t)nr * 8);
+    L.width = o; o += pm_lap_align((size_t)nr * 8);
+    L.ring = o; o += pm_lap_align((size_t)pm_ls_ring_cap(nr) * 2);
     L.per_item = o;
     return L;
 }
@@ -69,6 +91,9 @@ struct PmLapBatch {   // passed by value to kernels
     char *ws; PmLapLayout L;
     int32_t *col4row; long long *stats; double *total;
     int32_t *progress;   // [2] assignments made in the current / previous bidding round
+    long long max_bids;  // sparse auction: bid budget per warp
+    unsigned ring_cap;   // sparse auction: ticket ring capacity (power of two >= nr)
+    int ring_in_smem;
 };
 
 __device__ __forceinline__ PmLapView pm_lap_view(const PmLapBatch &B, int b) {
@@ -82,6 +107,8 @@ __device__ __forceinline__ PmLapView pm_lap_view(const PmLapBatch &B, int b) {
     V.colbest = (unsigned long long *)(w + B.L.colbest);
     V.free_lists = (int32_t *)(w + B.L.free_lists);
     V.counters = (int32_t *)(w + B.L.counters);
+    V.lcol = (int32_t *)(w + B.L.lcol); V.lcost = (float *)(w + B.L.lcost); V.tau = (double *)(w + B.L.tau);
+    V.width = (double *)(w + B.L.width); V.ring = (unsigned short *)(w + B.L.ring);
     V.stats = B.stats ? B.stats + (size_t)b * PM_LAP_STATS : nullptr;
     V.total = B.total + b;
     return V;
@@ -236,6 +263,349 @@ __global__ void __launch_bounds__(PM_LAP_BID_THREADS) pm_lap_bid_persistent(PmLa
     }
     if (gtid == 0)
         for (int b = 0; b < batch; ++b) pm_lap_view(B, b).counters[3] = round;
+}
+
+// ------------------------------------------------------------------------------------- phase 1 (sparse, asynchronous)
+// Exact epsilon = 0 auction over *certified candidate lists*.
+//
+// Lists.  For every row i a warp scans the dense cost row once; each lane keeps the 5 smallest
+// reduced values c_ij - v_j of the columns it visited.  tau_i = the smallest "5th value" over the 32
+// lanes; the list L_i = the (<= 128) kept entries with value <= tau_i, stored in the lane's own 4
+// slots (no compaction, no overflow).  Every column outside L_i then has c_ij - v_j >= tau_i, and
+// because prices only ever FALL in this algorithm that stays true forever:
+//        c_ij - v_j >= tau_i   for all j not in L_i.                                        (*)
+// (*) turns the list into an exact oracle for the dense row: if the best list value w1 is below
+// tau_i, it is the best over ALL columns, and min(w2, tau_i) is a lower bound of the true second
+// best, so bidding the increment gamma = min(w2, tau_i) - w1 keeps the new edge an exact arg-min of
+// its row (complementary slackness holds exactly; a smaller-than-possible increment is always valid).
+// If w1 >= tau_i the list is exhausted and the warp rebuilds it from the dense row at current prices:
+// one sweep that collects every column with c - v < tau_i + width_i (width_i = the value range the
+// previous list covered) into the 128 slots; columns that do not fit lower the new tau instead.
+//
+// Schedule.  ONE 1024-thread CTA per matrix: prices (f64) and the column owners (u16) live in shared
+// memory, the lists in global memory (L2 resident).  The 32 warps run independently, without any
+// barrier.  Rows are served first-in first-out: fresh rows 0..nr-1 from a counter, then displaced
+// owners through a ticket ring (FIFO order needs ~40 % fewer bids than following the displaced row
+// depth-first).  Per bid: 4 list entries per lane against the current prices, warp arg-min and
+// second-min with REDUX on order-preserving integer keys, and the lane that holds the winning column
+// commits under a per-column lock (the owner word, CAS to a sentinel): the price must still be the one
+// the bid was computed from, otherwise the bid is recomputed.  Other prices may have fallen in the
+// meantime, which only makes the true second-best larger, i.e. the committed increment smaller than
+// allowed: still exact.  A row whose bid would be a zero-increment steal is parked for phase 2 (this
+// is where epsilon = 0 auctions stall); at 8k that is 0-15 rows per matrix.
+#define PM_LS_NONE 0xFFFFu
+#define PM_LS_LOCKED 0xFFFEu
+#define PM_LS_MAX_ROWS 0xFFFDu
+#define PM_LS_EMPTY 0xFFFFu
+
+struct PmLsTop {           // the five smallest reduced values a lane has seen, ascending
+    double w[5];
+    int j[5];
+    float c[5];
+};
+
+__device__ __forceinline__ void pm_ls_top_init(PmLsTop &t) {
+#pragma unroll
+    for (int m = 0; m < 5; ++m) { t.w[m] = INFINITY; t.j[m] = -1; t.c[m] = 0.0f; }
+}
+
+__device__ __forceinline__ void pm_ls_top_push(PmLsTop &t, double w, int j, float c) {
+    if (w < t.w[4]) {      // strict: among equal values the earlier (lower) column stays in front
+        t.w[4] = w; t.j[4] = j; t.c[4] = c;
+#pragma unroll
+        for (int m = 4; m > 0; --m) {
+            if (t.w[m] < t.w[m - 1]) {
+                const double tw = t.w[m]; t.w[m] = t.w[m - 1]; t.w[m - 1] = tw;
+                const int tj = t.j[m]; t.j[m] = t.j[m - 1]; t.j[m - 1] = tj;
+                const float tc = t.c[m]; t.c[m] = t.c[m - 1]; t.c[m - 1] = tc;
+            }
+        }
+    }
+}
+
+// initial lists at zero prices: one warp per row, all SMs (float4 sweeps, ldc % 4 == 0)
+__global__ void __launch_bounds__(256) pm_ls_build_lists(PmLapBatch B) {
+    const PmLapView V = pm_lap_view(B, blockIdx.y);
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
+    for (int i = warp; i < B.nr; i += nwarps) {
+        const float *ci = V.cost + (size_t)i * B.ldc;
+        PmLsTop t;
+        pm_ls_top_init(t);
+#pragma unroll 4
+        for (int j0 = lane * 4; j0 < B.nc; j0 += 128) {
+            const float4 c4 = *reinterpret_cast<const float4 *>(ci + j0);
+            const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (j0 + e < B.nc) pm_ls_top_push(t, (double)cc[e], j0 + e, cc[e]);
+        }
+        double tmin = t.w[4], wmin = t.w[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+            wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+        }
+        reinterpret_cast<int4 *>(V.lcol + (size_t)i * PM_LS_K)[lane] =
+            make_int4(t.w[0] <= tmin ? t.j[0] : -1, t.w[1] <= tmin ? t.j[1] : -1, t.w[2] <= tmin ? t.j[2] : -1,
+                      t.w[3] <= tmin ? t.j[3] : -1);
+        reinterpret_cast<float4 *>(V.lcost + (size_t)i * PM_LS_K)[lane] = make_float4(t.c[0], t.c[1], t.c[2], t.c[3]);
+        if (lane == 0) {
+            V.tau[i] = tmin;
+            V.width[i] = (tmin < INFINITY && wmin < INFINITY) ? tmin - wmin : INFINITY;
+        }
+    }
+}
+
+// order-preserving 64-bit integer image of a double (so that REDUX.MIN on two 32-bit halves finds the minimum)
+__device__ __forceinline__ unsigned long long pm_ordkey(double x) {
+    const long long b = __double_as_longlong(x);
+    return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000LL));
+}
+__device__ __forceinline__ double pm_ordval(unsigned long long k) {
+    const long long b = (k & 0x8000000000000000ULL) ? (long long)(k ^ 0x8000000000000000ULL) : (long long)~k;
+    return __longlong_as_double(b);
+}
+__device__ __forceinline__ unsigned long long pm_warp_min_u64(unsigned long long k) {
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    return ((unsigned long long)mh << 32) | ml;
+}
+
+// Rebuild the list of one row at current prices (one warp): every column with c - v < limit goes into
+// the row's 128 slots in column order; what does not fit lowers tau.  Returns the number of entries
+// (uniform); the lane's own slots and the new tau / width come back in registers.
+__device__ __forceinline__ int pm_ls_refresh_row(const PmLapView &V, int row, const float *__restrict__ ci,
+                                                 const double *v, int nc, int lane, double limit, int4 &cj,
+                                                 float4 &cc, double &tau, double &wmin_out) {
+    int32_t *lcol = V.lcol + (size_t)row * PM_LS_K;
+    float *lcost = V.lcost + (size_t)row * PM_LS_K;
+    reinterpret_cast<int4 *>(lcol)[lane] = make_int4(-1, -1, -1, -1);
+    __syncwarp();
+    int count = 0;
+    double dropped = INFINITY, wmin = INFINITY;
+#pragma unroll 2
+    for (int j0 = lane * 4; j0 < ((nc + 127) & ~127); j0 += 128) {
+        float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j0 < nc) c4 = *reinterpret_cast<const float4 *>(ci + j0);
+        const float cs[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = j0 + e;
+            double w = INFINITY;
+            if (j < nc) w = (double)cs[e] - v[j];
+            wmin = fmin(wmin, w);
+            const bool hit = w < limit;
+            const unsigned hits = __ballot_sync(0xffffffffu, hit);
+            if (hits) {
+                const int pos = count + __popc(hits & ((1u << lane) - 1u));
+                if (hit) {
+                    if (pos < PM_LS_K) { lcol[pos] = j; lcost[pos] = cs[e]; }
+                    else dropped = fmin(dropped, w);
+                }
+                count += __popc(hits);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dropped = fmin(dropped, __shfl_xor_sync(0xffffffffu, dropped, o));
+        wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+    }
+    tau = fmin(limit, dropped);
+    wmin_out = wmin;
+    __syncwarp();
+    cj = __ldcg(reinterpret_cast<const int4 *>(lcol) + lane);
+    cc = __ldcg(reinterpret_cast<const float4 *>(lcost) + lane);
+    return count < PM_LS_K ? count : PM_LS_K;
+}
+
+enum { PM_LS_WON = 0, PM_LS_PARK = 1, PM_LS_RETRY = 2 };
+
+struct PmLsShared {
+    int fresh;              // next fresh row
+    unsigned head, tail;    // ring of displaced rows
+    unsigned long long stat[6];   // bids, refreshes, retries, parked, refresh cycles, (max) busy cycles
+    unsigned long long maxbids;
+};
+
+// dynamic shared memory: v f64[ncp] | owner u16[ncp] | ring u16[ring_cap] (ring_cap = 0: ring in global memory)
+__global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
+    extern __shared__ __align__(16) unsigned char pm_ls_smem[];
+    const PmLapView V = pm_lap_view(B, blockIdx.x);
+    const int nr = B.nr, nc = B.nc, ncp = B.ncp;
+    double *v = reinterpret_cast<double *>(pm_ls_smem);
+    unsigned short *owner = reinterpret_cast<unsigned short *>(v + ncp);
+    volatile unsigned short *ring = B.ring_in_smem ? (owner + ncp) : V.ring;
+    const unsigned ring_mask = B.ring_cap - 1;
+    __shared__ PmLsShared S;
+    const int t = threadIdx.x, lane = t & 31;
+
+    for (int j = t; j < ncp; j += blockDim.x) { v[j] = 0.0; owner[j] = PM_LS_NONE; }
+    for (unsigned q = t; q < B.ring_cap; q += blockDim.x) ring[q] = PM_LS_EMPTY;
+    for (int i = t; i < nr; i += blockDim.x) { V.col4row[i] = -1; V.u[i] = 0.0; }
+    if (t == 0) {
+        S.fresh = 0; S.head = 0; S.tail = 0; S.maxbids = 0;
+        for (int k = 0; k < 6; ++k) S.stat[k] = 0;
+    }
+    __syncthreads();
+
+    long long bids = 0, refreshes = 0, retries = 0, parked = 0, refresh_cycles = 0;
+    const long long t_begin = clock64();
+    int carry = -1;          // displaced owner this warp continues with (only when nothing is queued)
+    while (bids < B.max_bids) {
+        // ---- next row: fresh rows first, then displaced owners in FIFO order
+        int row = carry;
+        carry = -1;
+        if (row < 0) {
+            if (lane == 0) {
+                if (*(volatile int *)&S.fresh < nr) {
+                    const int r = atomicAdd(&S.fresh, 1);
+                    if (r < nr) row = r;
+                }
+                while (row < 0) {
+                    const unsigned h = *(volatile unsigned *)&S.head, tl = *(volatile unsigned *)&S.tail;
+                    if ((int)(tl - h) <= 0) break;                       // nothing queued: this warp is done
+                    if (atomicCAS(&S.head, h, h + 1u) != h) continue;
+                    unsigned short x;
+                    do { x = ring[h & ring_mask]; } while (x == PM_LS_EMPTY);   // slot reserved, value in flight
+                    ring[h & ring_mask] = PM_LS_EMPTY;
+                    row = x;
+                }
+            }
+            row = __shfl_sync(0xffffffffu, row, 0);
+            if (row < 0) break;
+        }
+        int4 cj = __ldcg(reinterpret_cast<const int4 *>(V.lcol + (size_t)row * PM_LS_K) + lane);
+        float4 cc = __ldcg(reinterpret_cast<const float4 *>(V.lcost + (size_t)row * PM_LS_K) + lane);
+        double tau = __ldcg(V.tau + row);
+        bool fresh = false;
+        int result, prev = PM_LS_NONE;
+        while (true) {
+            // lane-local: reduced values of its 4 slots at the current prices, branch-free
+            const int js[4] = {cj.x, cj.y, cj.z, cj.w};
+            const float cs[4] = {cc.x, cc.y, cc.z, cc.w};
+            double vs[4], ws[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                vs[e] = *reinterpret_cast<volatile double *>(&v[js[e] < 0 ? 0 : js[e]]);
+                const double w = (double)cs[e] - vs[e];
+                ws[e] = js[e] < 0 ? INFINITY : w;
+            }
+            // smallest and second smallest of four: 7 min/max
+            const double lo01 = fmin(ws[0], ws[1]), hi01 = fmax(ws[0], ws[1]);
+            const double lo23 = fmin(ws[2], ws[3]), hi23 = fmax(ws[2], ws[3]);
+            const double w1 = fmin(lo01, lo23);
+            const double w2 = fmin(fmax(lo01, lo23), fmin(hi01, hi23));
+            // warp: best value (REDUX on order-preserving keys), one holder lane, second best
+            const unsigned long long k1 = pm_ordkey(w1);
+            const unsigned long long kb = pm_warp_min_u64(k1);
+            const unsigned holders = __ballot_sync(0xffffffffu, k1 == kb);
+            const int hl = __ffs(holders) - 1;
+            const bool holder = lane == hl;
+            const double bw = pm_ordval(kb);
+            // smallest value that does not belong to the winning slot
+            const double sw = pm_ordval(pm_warp_min_u64(pm_ordkey(holder ? w2 : w1)));
+            if (!(bw < INFINITY)) { result = PM_LS_PARK; break; }                 // no finite entry: phase 2 reports it
+            if (!(bw < tau) && !(fresh && bw <= tau)) {
+                // list exhausted: cannot certify the best column -> rebuild from the dense row
+                const long long t0 = clock64();
+                double width = __ldcg(V.width + row), wmin;
+                if (!(width > 0.0) || !(width < INFINITY)) width = fabs(tau) * 1e-3 + 1e-300;
+                int n = pm_ls_refresh_row(V, row, V.cost + (size_t)row * B.ldc, v, nc, lane, tau + width, cj, cc, tau, wmin);
+                if (n < 8 && wmin < INFINITY) {        // window too narrow (prices moved a lot): centre it on the minimum
+                    width *= 4.0;
+                    n = pm_ls_refresh_row(V, row, V.cost + (size_t)row * B.ldc, v, nc, lane, wmin + width, cj, cc, tau, wmin);
+                } else if (n >= PM_LS_K) {
+                    width *= 0.5;
+                }
+                if (lane == 0) { V.tau[row] = tau; V.width[row] = width; }
+                fresh = true;
+                ++refreshes;
+                refresh_cycles += clock64() - t0;
+                continue;
+            }
+            double gamma = fmin(sw, tau) - bw;    // certified lower bound of the true increment
+            if (!(gamma > 0.0)) gamma = 0.0;
+            result = PM_LS_RETRY;
+            if (holder) {
+                const bool m0 = ws[0] == w1, m1 = ws[1] == w1, m2 = ws[2] == w1;
+                const int bj = m0 ? js[0] : m1 ? js[1] : m2 ? js[2] : js[3];
+                const double v1 = m0 ? vs[0] : m1 ? vs[1] : m2 ? vs[2] : vs[3];
+                unsigned short *p = &owner[bj];
+                unsigned short old;
+                while (true) {      // lock the column: the owner word doubles as the lock
+                    old = *reinterpret_cast<volatile unsigned short *>(p);
+                    if (old != PM_LS_LOCKED && atomicCAS(p, old, (unsigned short)PM_LS_LOCKED) == old) break;
+                }
+                const double vj = *reinterpret_cast<volatile double *>(&v[bj]);
+                if (vj != v1) {
+                    *reinterpret_cast<volatile unsigned short *>(p) = old;                 // price moved: recompute
+                } else if (gamma == 0.0 && old != PM_LS_NONE) {
+                    *reinterpret_cast<volatile unsigned short *>(p) = old;                 // zero-increment steal: park
+                    result = PM_LS_PARK;
+                } else {
+                    *reinterpret_cast<volatile double *>(&v[bj]) = vj - gamma;
+                    __threadfence_block();
+                    *reinterpret_cast<volatile unsigned short *>(p) = (unsigned short)row;  // releases the lock
+                    result = PM_LS_WON;
+                    prev = old;
+                    if (old != PM_LS_NONE) {
+                        // displaced owner bids again: behind everything that is queued (FIFO needs fewer
+                        // bids than depth-first), or right away in this warp when nothing is queued
+                        const bool queued = *(volatile int *)&S.fresh < nr ||
+                                            (int)(*(volatile unsigned *)&S.tail - *(volatile unsigned *)&S.head) > 0;
+                        if (queued) {
+                            const unsigned pos = atomicAdd(&S.tail, 1u);
+                            ring[pos & ring_mask] = old;
+                            prev = PM_LS_NONE;
+                        }
+                    }
+                }
+            }
+            result = __shfl_sync(0xffffffffu, result, hl);
+            prev = __shfl_sync(0xffffffffu, prev, hl);
+            if (result != PM_LS_RETRY) break;
+            ++retries;
+        }
+        ++bids;
+        if (result == PM_LS_PARK) ++parked;
+        else if (prev != PM_LS_NONE) carry = prev;
+    }
+    if (lane == 0) {
+        atomicAdd(&S.stat[0], (unsigned long long)bids);
+        atomicAdd(&S.stat[1], (unsigned long long)refreshes);
+        atomicAdd(&S.stat[2], (unsigned long long)retries);
+        atomicAdd(&S.stat[3], (unsigned long long)parked);
+        atomicAdd(&S.stat[4], (unsigned long long)refresh_cycles);
+        atomicMax(&S.stat[5], (unsigned long long)(clock64() - t_begin));
+        atomicMax(&S.maxbids, (unsigned long long)bids);
+    }
+    __syncthreads();
+    // hand the state to phase 2: prices, owners, row duals u_i = c_ij - v_j of the assigned edge
+    for (int j = t; j < ncp; j += blockDim.x) {
+        const unsigned short r = owner[j];
+        if (j < nc) {
+            V.v[j] = v[j];
+            V.row4col[j] = (r == PM_LS_NONE) ? -1 : (int)r;
+            if (r != PM_LS_NONE) {
+                V.col4row[r] = j;
+                V.u[r] = (double)V.cost[(size_t)r * B.ldc + j] - v[j];
+            }
+        }
+    }
+    if (t == 0) {
+        V.counters[3] = (int32_t)(S.maxbids > 0x7fffffffull ? 0x7fffffffull : S.maxbids);
+        if (V.stats) {
+            V.stats[PM_LAP_STAT_BIDS] = (long long)S.stat[0];
+            V.stats[PM_LAP_STAT_REFRESHES] = (long long)S.stat[1];
+            V.stats[PM_LAP_STAT_RETRIES] = (long long)S.stat[2];
+            V.stats[PM_LAP_STAT_PARKED] = (long long)S.stat[3];
+            V.stats[PM_LAP_STAT_REFRESH_CYCLES] = (long long)S.stat[4];
+            V.stats[PM_LAP_STAT_AUCTION_CYCLES] = (long long)S.stat[5];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------- phase 2
@@ -435,7 +805,9 @@ static int pm_lap_launch_sap(const PmLapBatch &B, int batch, int threads, cudaSt
     return PM_OK;
 }
 
-extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ldc, int max_bid_rounds,
+static size_t pm_ls_smem_bytes(int ncp) { return (size_t)ncp * (sizeof(double) + sizeof(unsigned short)); }
+
+extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ldc, int max_bid_rounds, int algorithm,
                             int32_t *col4row, double *total, int64_t *stats, void *workspace,
                             size_t workspace_bytes, void *stream) {
     PM_REQUIRE(cost && col4row && total && workspace, "null pointer");
@@ -444,6 +816,7 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
     PM_REQUIRE(ldc >= nc && ldc % 4 == 0, "ldc must be >= nc and a multiple of 4");
     PM_REQUIRE((reinterpret_cast<size_t>(cost) & 15) == 0, "cost must be 16-byte aligned");
     PM_REQUIRE(max_bid_rounds >= 0, "max_bid_rounds < 0");
+    PM_REQUIRE(algorithm >= PM_LAP_ALGO_AUTO && algorithm <= PM_LAP_ALGO_DENSE_AUCTION, "unknown algorithm");
     if (nc > 24 * PM_LAP_MAX_THREADS) {
         pm_set_error("pm_lap_solve: nc = %d > %d columns not supported by the single-CTA path", nc,
                      24 * PM_LAP_MAX_THREADS);
@@ -461,12 +834,38 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
     B.progress = (int32_t *)workspace;
     B.ws = (char *)workspace + 256;
     B.col4row = col4row; B.stats = (long long *)stats; B.total = total;
+    // one "round" of the sparse auction = a budget of one bid per row, spread over the 32 warps
+    B.max_bids = ((long long)max_bid_rounds * nr + 31) / 32;
+
+    int dev = 0, smem_optin = 0;
+    PM_CUDA_TRY(cudaGetDevice(&dev));
+    PM_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    size_t ls_smem = pm_ls_smem_bytes(B.ncp);
+    const bool sparse_fits = nr <= (int)PM_LS_MAX_ROWS && ls_smem + 2048 <= (size_t)smem_optin;
+    B.ring_cap = pm_ls_ring_cap(nr);
+    B.ring_in_smem = ls_smem + (size_t)B.ring_cap * 2 + 2048 <= (size_t)smem_optin;
+    if (B.ring_in_smem) ls_smem += (size_t)B.ring_cap * 2;
+    if (algorithm == PM_LAP_ALGO_SPARSE_AUCTION && !sparse_fits) {
+        pm_set_error("pm_lap_solve: %d x %d does not fit the sparse auction (prices in shared memory)", nr, nc);
+        return PM_ERR_UNSUPPORTED;
+    }
+    if (algorithm == PM_LAP_ALGO_AUTO) algorithm = sparse_fits ? PM_LAP_ALGO_SPARSE_AUCTION : PM_LAP_ALGO_DENSE_AUCTION;
 
     pm_lap_init_kernel<<<dim3(32, batch), 256, 0, s>>>(B);
     PM_LAUNCH_CHECK();
-    if (max_bid_rounds > 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        PM_CUDA_TRY(cudaGetDevice(&dev));
+    if (max_bid_rounds > 0 && algorithm == PM_LAP_ALGO_SPARSE_AUCTION) {
+        int sms = 0;
+        PM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        int blocks = (nr + 7) / 8;                       // 8 warps (rows) per CTA per sweep
+        const int cap = (sms * 8 + batch - 1) / batch;   // ~8 resident CTAs per SM over the whole batch
+        if (blocks > cap) blocks = cap;
+        pm_ls_build_lists<<<dim3(blocks, batch), 256, 0, s>>>(B);
+        PM_LAUNCH_CHECK();
+        PM_CUDA_TRY(cudaFuncSetAttribute(pm_ls_auction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem));
+        pm_ls_auction_kernel<<<batch, 1024, ls_smem, s>>>(B);
+        PM_LAUNCH_CHECK();
+    } else if (max_bid_rounds > 0) {
+        int sms = 0, per_sm = 0;
         PM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         PM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm_lap_bid_persistent, PM_LAP_BID_THREADS, 0));
         if (per_sm < 1) { pm_set_error("pm_lap_solve: bidding kernel does not fit on an SM"); return PM_ERR_CUDA; }

@@ -116,7 +116,7 @@ def chi2_cost(a, b, out=None, row_begin=0, row_end=None):
     return out
 
 
-def lap_solve(cost, nr, nc, max_bid_rounds=2048):
+def lap_solve(cost, nr, nc, max_bid_rounds=2048, algorithm=0):
     """cost [batch, nr, ldc] float32 (nr <= nc) -> col4row [batch, nr] int32, total [batch] f64, stats [batch, 8] i64."""
     torch = _torch()
     if cost.dim() == 2:
@@ -128,7 +128,7 @@ def lap_solve(cost, nr, nc, max_bid_rounds=2048):
     stats = torch.zeros((batch, LAP_STATS), dtype=torch.int64, device=cost.device)
     nbytes = load().pm_lap_workspace_bytes(batch, nr, nc)
     ws = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=cost.device)
-    check(load().pm_lap_solve(ptr(cost), batch, nr, nc, ldc, int(max_bid_rounds), ptr(col4row), ptr(total), ptr(stats),
+    check(load().pm_lap_solve(ptr(cost), batch, nr, nc, ldc, int(max_bid_rounds), int(algorithm), ptr(col4row), ptr(total), ptr(stats),
                               ptr(ws), nbytes, stream_ptr()), "pm_lap_solve")
     return col4row, total, stats
 

@@ -7,11 +7,12 @@ from . import device as D
 __all__ = ["linear_sum_assignment"]
 
 
-def linear_sum_assignment(cost_matrix, maximize=False, return_stats=False, max_bid_rounds=2048):
+def linear_sum_assignment(cost_matrix, maximize=False, return_stats=False, max_bid_rounds=2048, algorithm=0):
     """Minimum-cost assignment of a dense (nr, nc) matrix -> (row_ind, col_ind) int64 arrays.
 
     The matrix is solved as float32 values with float64 duals (optimal for the float32-rounded
     matrix).  Tall matrices are solved through the transpose, as scipy does.
+    algorithm: 0 auto, 1 sparse asynchronous auction, 2 dense grid-wide auction (PM_LAP_ALGO_*).
     """
     torch = D._torch()
     c = np.asarray(cost_matrix)
@@ -31,7 +32,7 @@ def linear_sum_assignment(cost_matrix, maximize=False, return_stats=False, max_b
     ldc = (nc + 3) // 4 * 4
     buf = np.zeros((1, nr, ldc), dtype=np.float32)
     buf[0, :, :nc] = c
-    col4row, total, stats = D.lap_solve(torch.from_numpy(buf).cuda(), nr, nc, max_bid_rounds)
+    col4row, total, stats = D.lap_solve(torch.from_numpy(buf).cuda(), nr, nc, max_bid_rounds, algorithm)
     col = col4row[0].cpu().numpy().astype(np.int64)
     st = stats[0].cpu().numpy()
     if st[4] != 0:
@@ -42,5 +43,7 @@ def linear_sum_assignment(cost_matrix, maximize=False, return_stats=False, max_b
         rows, col = col[order], rows[order]
     if return_stats:
         return rows, col, dict(total=float(total.item()), bid_rounds=int(st[0]), rows_after_bidding=int(st[1]),
-                               augmentations=int(st[2]), dijkstra_steps=int(st[3]))
+                               augmentations=int(st[2]), dijkstra_steps=int(st[3]), bids=int(st[5]),
+                               refreshes=int(st[6]), retries=int(st[7]), parked=int(st[8]),
+                               refresh_cycles=int(st[9]), auction_cycles=int(st[10]))
     return rows, col

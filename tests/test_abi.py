@@ -42,7 +42,7 @@ def test_argument_validation_is_host_side():
     lib = _lib.load()
     assert lib.pm_cloud_stats(None, 10, None, None) == -1
     assert b"null pointer" in lib.pm_last_error_string()
-    assert lib.pm_lap_solve(None, 1, 4, 4, 4, 0, None, None, None, None, 0, None) == -1
+    assert lib.pm_lap_solve(None, 1, 4, 4, 4, 0, 0, None, None, None, None, 0, None) == -1
     with pytest.raises(ValueError):
         _lib.check(-1, "x")
 

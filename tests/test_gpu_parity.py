@@ -209,24 +209,40 @@ def _check_lap(O, cost, **kw):
 
 
 @pytest.mark.parametrize("shape", [(1, 1), (1, 7), (2, 2), (5, 9), (9, 5), (64, 64), (100, 257), (300, 300), (500, 1200)])
-@pytest.mark.parametrize("rounds", [0, 3, 128])
-def test_lap_random_matrices(O, torch, shape, rounds):
+@pytest.mark.parametrize("rounds,algo", [(0, 0), (3, 1), (128, 1), (3, 2), (128, 2)])
+def test_lap_random_matrices(O, torch, shape, rounds, algo):
     rng = np.random.default_rng(shape[0] * 7 + shape[1])
     cost = rng.random(shape)
-    (r, c), (ro, co), st = _check_lap(O, cost, max_bid_rounds=rounds)
+    (r, c), (ro, co), st = _check_lap(O, cost, max_bid_rounds=rounds, algorithm=algo)
     assert np.array_equal(c, co)              # continuous random costs: the optimum is unique
 
 
-def test_lap_ties_and_structure(O, torch):
+@pytest.mark.parametrize("algo", [1, 2])
+def test_lap_ties_and_structure(O, torch, algo):
     """Integer costs (many equal-cost optima), constant matrix, permuted diagonal, negative entries."""
     rng = np.random.default_rng(3)
-    _check_lap(O, rng.integers(0, 5, size=(60, 80)).astype(float))
-    _check_lap(O, np.ones((17, 17)))
+    _check_lap(O, rng.integers(0, 5, size=(60, 80)).astype(float), algorithm=algo)
+    _check_lap(O, rng.integers(0, 3, size=(300, 700)).astype(float), algorithm=algo)
+    _check_lap(O, np.ones((17, 17)), algorithm=algo)
     perm = rng.permutation(200)
     cost = np.ones((200, 200)); cost[np.arange(200), perm] = 0.0
-    (r, c), _, _ = _check_lap(O, cost)
+    (r, c), _, _ = _check_lap(O, cost, algorithm=algo)
     assert np.array_equal(c, perm)
-    _check_lap(O, rng.normal(size=(50, 70)))
+    _check_lap(O, rng.normal(size=(50, 70)), algorithm=algo)
+    # all rows want the same few columns: long price wars, list refreshes
+    cost = rng.random((400, 900)) + 5.0
+    cost[:, :20] -= 5.0
+    _check_lap(O, cost, algorithm=algo)
+
+
+def test_lap_sparse_auction_stats(O, torch):
+    """The sparse auction leaves (almost) nothing to the augmenting-path phase on a shape-context-like matrix."""
+    rng = np.random.default_rng(11)
+    a, b = rng.random((600, 40)), rng.random((800, 40))
+    cost = ((a[:, None, :] - b[None, :, :]) ** 2).sum(-1)
+    (r, c), (ro, co), st = _check_lap(O, cost, algorithm=1)
+    assert np.array_equal(c, co)
+    assert st["bids"] >= 600 and st["augmentations"] <= 30, st
 
 
 def test_lap_on_reference_cost_matrices(O, torch):
