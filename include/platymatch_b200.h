@@ -134,6 +134,7 @@ int pm_chi2_cost(const float *a_t, int lda, const uint32_t *a_mask, int n1, cons
 #define PM_LAP_STAT_PARKED 8          /* sparse auction: rows parked for phase 2 (zero-increment steals) */
 #define PM_LAP_STAT_REFRESH_CYCLES 9  /* sparse auction: SM cycles spent rebuilding lists, summed over warps */
 #define PM_LAP_STAT_AUCTION_CYCLES 10 /* sparse auction: SM cycles of the longest-running warp */
+#define PM_LAP_STAT_BULK_BIDS 11      /* sparse auction: bids made by the multi-SM bulk kernel */
 #define PM_LAP_ALGO_AUTO 0
 #define PM_LAP_ALGO_SPARSE_AUCTION 1
 #define PM_LAP_ALGO_DENSE_AUCTION 2

@@ -24,6 +24,7 @@
 // Costs are the float32 matrix produced by K3; duals, distances and the total are float64, so the
 // result is optimal for the matrix given (up to float64 rounding, like scipy on the same values).
 #include <limits.h>
+#include <stdlib.h>
 #include <cooperative_groups.h>
 #include "pm_common.cuh"
 
@@ -32,6 +33,8 @@ namespace cg = cooperative_groups;
 #define PM_LAP_BID_THREADS 1024
 #define PM_LAP_CPT 8
 #define PM_LAP_MAX_THREADS 1024
+
+struct __align__(16) PmLsCell { double price; unsigned owner; unsigned pad; };
 
 struct PmLapView {
     const float *cost;      // [nr][ldc]
@@ -47,7 +50,9 @@ struct PmLapView {
     float *lcost;           // [nr][PM_LS_K] their costs
     double *tau;            // [nr] every column outside the list has c - v >= tau, forever
     double *width;          // [nr] value range the list covered when it was built (refresh window)
-    unsigned short *ring;   // [ring_cap] ticket ring of displaced rows when it does not fit in shared memory
+    unsigned short *ring;   // [ring_cap] ring of displaced rows when it does not fit in shared memory (tail kernel)
+    unsigned *ring32;       // [ring_cap] ring of displaced rows of the bulk kernel
+    struct PmLsCell *cell;  // [nc] {price, owner} of the bulk kernel
     long long *stats;       // [PM_LAP_STATS] or null
     double *total;
 };
@@ -55,9 +60,17 @@ struct PmLapView {
 static inline size_t pm_lap_align(size_t x) { return (x + 255) & ~(size_t)255; }
 
 #define PM_LS_K 128          // candidate-list slots per row: 32 lanes x 4
+// per-matrix int32 counters of the bulk auction kernel (PmLapView::counters)
+#define PM_LS_CTR_FRESH 5
+#define PM_LS_CTR_HEAD 6
+#define PM_LS_CTR_TAIL 7
+#define PM_LS_CTR_LIVE 8
+#define PM_LS_CTR_BIDS 9
+#define PM_LS_CTR_RETRIES 10
+#define PM_LS_CTR_DROPPED 11
 
 struct PmLapLayout {
-    size_t u, v, row4col, bid_col, bid_gamma, colbest, free_lists, counters, lcol, lcost, tau, width, ring, per_item;
+    size_t u, v, row4col, bid_col, bid_gamma, colbest, free_lists, counters, lcol, lcost, tau, width, ring, ring32, cell, per_item;
 };
 
 static unsigned pm_ls_ring_cap(int nr) {   // power of two >= nr: the ring can hold every row at once
@@ -82,6 +95,8 @@ static PmLapLayout pm_lap_layout(int nr, int nc) {
     L.tau = o; o += pm_lap_align((size_t)nr * 8);
     L.width = o; o += pm_lap_align((size_t)nr * 8);
     L.ring = o; o += pm_lap_align((size_t)pm_ls_ring_cap(nr) * 2);
+    L.ring32 = o; o += pm_lap_align((size_t)pm_ls_ring_cap(nr) * 4);
+    L.cell = o; o += pm_lap_align((size_t)nc * 16);
     L.per_item = o;
     return L;
 }
@@ -92,6 +107,10 @@ struct PmLapBatch {   // passed by value to kernels
     int32_t *col4row; long long *stats; double *total;
     int32_t *progress;   // [2] assignments made in the current / previous bidding round
     long long max_bids;  // sparse auction: bid budget per warp
+    int stop_live;       // sparse auction: stop carrying displaced rows once this few warps are still bidding
+    int bulk_stop_live;  // bulk kernel: stop once this few warps (of bulk_warps) are still bidding
+    int bulk_warps;
+    int bulk_patience;   // bulk kernel: polls (200 ns apart) a warp waits for its ring slot before it leaves
     unsigned ring_cap;   // sparse auction: ticket ring capacity (power of two >= nr)
     int ring_in_smem;
 };
@@ -109,6 +128,7 @@ __device__ __forceinline__ PmLapView pm_lap_view(const PmLapBatch &B, int b) {
     V.counters = (int32_t *)(w + B.L.counters);
     V.lcol = (int32_t *)(w + B.L.lcol); V.lcost = (float *)(w + B.L.lcost); V.tau = (double *)(w + B.L.tau);
     V.width = (double *)(w + B.L.width); V.ring = (unsigned short *)(w + B.L.ring);
+    V.ring32 = (unsigned *)(w + B.L.ring32); V.cell = (PmLsCell *)(w + B.L.cell);
     V.stats = B.stats ? B.stats + (size_t)b * PM_LAP_STATS : nullptr;
     V.total = B.total + b;
     return V;
@@ -119,9 +139,15 @@ __global__ void pm_lap_init_kernel(PmLapBatch B) {
     const PmLapView V = pm_lap_view(B, blockIdx.y);
     const int t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     for (int i = t; i < B.nr; i += stride) { V.u[i] = 0.0; V.col4row[i] = -1; V.free_lists[i] = i; V.bid_col[i] = -1; }
-    for (int j = t; j < B.ncp; j += stride) { V.v[j] = 0.0; V.row4col[j] = -1; V.colbest[j] = 0ull; }
+    for (int j = t; j < B.ncp; j += stride) {
+        V.v[j] = 0.0; V.row4col[j] = -1; V.colbest[j] = 0ull;
+        V.cell[j].price = 0.0; V.cell[j].owner = 0xFFFFFFFFu; V.cell[j].pad = 0u;
+    }
+    for (unsigned q = t; q < B.ring_cap; q += stride) V.ring32[q] = 0xFFFFFFFFu;
     if (t == 0) {
         V.counters[0] = B.nr; V.counters[1] = 0; V.counters[2] = 0; V.counters[3] = 0; V.counters[4] = 0;
+        for (int k = 5; k < 16; ++k) V.counters[k] = 0;
+        V.counters[PM_LS_CTR_LIVE] = B.bulk_warps;
         B.progress[0] = 0; B.progress[1] = 0;
         if (V.stats) for (int k = 0; k < PM_LAP_STATS; ++k) V.stats[k] = 0;
     }
@@ -385,26 +411,40 @@ __device__ __forceinline__ int pm_ls_refresh_row(const PmLapView &V, int row, co
     __syncwarp();
     int count = 0;
     double dropped = INFINITY, wmin = INFINITY;
-#pragma unroll 2
-    for (int j0 = lane * 4; j0 < ((nc + 127) & ~127); j0 += 128) {
-        float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j0 < nc) c4 = *reinterpret_cast<const float4 *>(ci + j0);
-        const float cs[4] = {c4.x, c4.y, c4.z, c4.w};
+    for (int base = 0; base < nc; base += 512) {       // 4 sweeps per trip: the four row loads are in flight together
+        float4 c4[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int j = j0 + e;
-            double w = INFINITY;
-            if (j < nc) w = (double)cs[e] - v[j];
-            wmin = fmin(wmin, w);
-            const bool hit = w < limit;
-            const unsigned hits = __ballot_sync(0xffffffffu, hit);
-            if (hits) {
-                const int pos = count + __popc(hits & ((1u << lane) - 1u));
-                if (hit) {
-                    if (pos < PM_LS_K) { lcol[pos] = j; lcost[pos] = cs[e]; }
-                    else dropped = fmin(dropped, w);
+        for (int u = 0; u < 4; ++u) {
+            const int j0 = base + u * 128 + lane * 4;
+            c4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j0 < nc) c4[u] = *reinterpret_cast<const float4 *>(ci + j0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j0 = base + u * 128 + lane * 4;
+            const float cs[4] = {c4[u].x, c4[u].y, c4[u].z, c4[u].w};
+            double w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j0 + e;
+                w[e] = (j < nc) ? (double)cs[e] - v[j] : INFINITY;
+                wmin = fmin(wmin, w[e]);
+            }
+            const bool any = (w[0] < limit) || (w[1] < limit) || (w[2] < limit) || (w[3] < limit);
+            if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool hit = w[e] < limit;
+                    const unsigned hits = __ballot_sync(0xffffffffu, hit);
+                    if (hits) {
+                        const int pos = count + __popc(hits & ((1u << lane) - 1u));
+                        if (hit) {
+                            if (pos < PM_LS_K) { lcol[pos] = j0 + e; lcost[pos] = cs[e]; }
+                            else dropped = fmin(dropped, w[e]);
+                        }
+                        count += __popc(hits);
+                    }
                 }
-                count += __popc(hits);
             }
         }
     }
@@ -421,11 +461,122 @@ __device__ __forceinline__ int pm_ls_refresh_row(const PmLapView &V, int row, co
     return count < PM_LS_K ? count : PM_LS_K;
 }
 
+
 enum { PM_LS_WON = 0, PM_LS_PARK = 1, PM_LS_RETRY = 2 };
+
+// ---- bulk phase: the same certified bids, spread over many SMs --------------------------------------
+// While thousands of rows are free the auction is throughput-bound, so the bulk of the bids runs on
+// `bulk_warps` warps per matrix all over the GPU.  Prices and owners live in global memory as 16-byte
+// cells {price, owner}; a bid is committed with ONE 128-bit compare-and-swap on the cell (expected =
+// the price the bid was computed from and the owner just read), so price and owner always change
+// together and no lock is needed.  Rows whose list is exhausted, zero-increment steals, and whatever
+// is still queued when the parallelism has collapsed are simply left free: the tail kernel below
+// (shared-memory prices, one CTA) picks them up.
+__device__ __forceinline__ bool pm_ls_cas128(PmLsCell *addr, double exp_price, unsigned exp_owner, double new_price,
+                                             unsigned new_owner) {
+    unsigned long long elo = (unsigned long long)__double_as_longlong(exp_price), ehi = (unsigned long long)exp_owner;
+    unsigned long long dlo = (unsigned long long)__double_as_longlong(new_price), dhi = (unsigned long long)new_owner;
+    unsigned long long rlo, rhi;
+    asm volatile(
+        "{\n\t.reg .b128 e, d, r;\n\tmov.b128 e, {%2, %3};\n\tmov.b128 d, {%4, %5};\n\t"
+        "atom.acq_rel.gpu.global.cas.b128 r, [%6], e, d;\n\tmov.b128 {%0, %1}, r;\n\t}"
+        : "=l"(rlo), "=l"(rhi)
+        : "l"(elo), "l"(ehi), "l"(dlo), "l"(dhi), "l"(addr)
+        : "memory");
+    return rlo == elo && rhi == ehi;
+}
+
+__global__ void __launch_bounds__(256) pm_ls_bulk_kernel(PmLapBatch B, int ctas_per_matrix) {
+    const PmLapView V = pm_lap_view(B, blockIdx.x / ctas_per_matrix);
+    const int nr = B.nr, lane = threadIdx.x & 31;
+    PmLsCell *cell = V.cell;
+    volatile unsigned *ring = V.ring32;
+    const unsigned ring_mask = B.ring_cap - 1;
+    volatile int *ctr = V.counters;
+    int bids = 0, retries = 0, dropped = 0;
+    while (bids < B.max_bids) {
+        int row = -1;
+        if (lane == 0) {
+            if (ctr[PM_LS_CTR_FRESH] < nr) {
+                const int r = atomicAdd(&V.counters[PM_LS_CTR_FRESH], 1);
+                if (r < nr) row = r;
+            }
+            if (row < 0 && ctr[PM_LS_CTR_LIVE] > B.bulk_stop_live) {
+                // ticket pop: slots fill in ticket order; a warp that waits too long for its slot leaves (the
+                // parallelism has collapsed) - a row that later lands in an abandoned slot simply stays free
+                const unsigned ticket = atomicAdd((unsigned *)&V.counters[PM_LS_CTR_HEAD], 1u);
+                for (int spin = 0; spin < B.bulk_patience; ++spin) {
+                    const unsigned x = ring[ticket & ring_mask];
+                    if (x != 0xFFFFFFFFu) { ring[ticket & ring_mask] = 0xFFFFFFFFu; row = (int)x; break; }
+                    if (ctr[PM_LS_CTR_LIVE] <= B.bulk_stop_live) break;
+                    __nanosleep(200);
+                }
+            }
+        }
+        row = __shfl_sync(0xffffffffu, row, 0);
+        if (row < 0) break;
+        const int4 cj = __ldcg(reinterpret_cast<const int4 *>(V.lcol + (size_t)row * PM_LS_K) + lane);
+        const float4 cc = __ldcg(reinterpret_cast<const float4 *>(V.lcost + (size_t)row * PM_LS_K) + lane);
+        const double tau = __ldcg(V.tau + row);
+        const int js[4] = {cj.x, cj.y, cj.z, cj.w};
+        const float cs[4] = {cc.x, cc.y, cc.z, cc.w};
+        bool won = false;
+        while (true) {
+            double vs[4], ws[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                vs[e] = *reinterpret_cast<volatile double *>(&cell[js[e] < 0 ? 0 : js[e]].price);
+                const double w = (double)cs[e] - vs[e];
+                ws[e] = js[e] < 0 ? INFINITY : w;
+            }
+            const double lo01 = fmin(ws[0], ws[1]), hi01 = fmax(ws[0], ws[1]);
+            const double lo23 = fmin(ws[2], ws[3]), hi23 = fmax(ws[2], ws[3]);
+            const double w1 = fmin(lo01, lo23);
+            const double w2 = fmin(fmax(lo01, lo23), fmin(hi01, hi23));
+            const unsigned long long k1 = pm_ordkey(w1);
+            const unsigned long long kb = pm_warp_min_u64(k1);
+            const int hl = __ffs(__ballot_sync(0xffffffffu, k1 == kb)) - 1;
+            const bool holder = lane == hl;
+            const double bw = pm_ordval(kb);
+            const double sw = pm_ordval(pm_warp_min_u64(pm_ordkey(holder ? w2 : w1)));
+            if (!(bw < tau)) break;                         // list exhausted (or no finite entry): tail kernel
+            double gamma = fmin(sw, tau) - bw;
+            if (!(gamma > 0.0)) gamma = 0.0;
+            int result = PM_LS_RETRY;
+            if (holder) {
+                const bool m0 = ws[0] == w1, m1 = ws[1] == w1, m2 = ws[2] == w1;
+                const int bj = m0 ? js[0] : m1 ? js[1] : m2 ? js[2] : js[3];
+                const double v1 = m0 ? vs[0] : m1 ? vs[1] : m2 ? vs[2] : vs[3];
+                const unsigned own = *reinterpret_cast<volatile unsigned *>(&cell[bj].owner);
+                if (gamma == 0.0 && own != 0xFFFFFFFFu) result = PM_LS_PARK;            // zero-increment steal
+                else if (pm_ls_cas128(&cell[bj], v1, own, v1 - gamma, (unsigned)row)) {
+                    result = PM_LS_WON;
+                    if (own != 0xFFFFFFFFu) {                                           // displaced owner: queue it
+                        const unsigned pos = atomicAdd((unsigned *)&V.counters[PM_LS_CTR_TAIL], 1u);
+                        ring[pos & ring_mask] = own;
+                    }
+                }
+            }
+            result = __shfl_sync(0xffffffffu, result, hl);
+            if (result == PM_LS_WON) { won = true; break; }
+            if (result == PM_LS_PARK) break;
+            ++retries;
+        }
+        ++bids;
+        if (!won) ++dropped;
+    }
+    if (lane == 0) {
+        atomicSub(&V.counters[PM_LS_CTR_LIVE], 1);
+        atomicAdd(&V.counters[PM_LS_CTR_BIDS], bids);
+        atomicAdd(&V.counters[PM_LS_CTR_RETRIES], retries);
+        atomicAdd(&V.counters[PM_LS_CTR_DROPPED], dropped);
+    }
+}
 
 struct PmLsShared {
     int fresh;              // next fresh row
     unsigned head, tail;    // ring of displaced rows
+    int live;               // warps still bidding
     unsigned long long stat[6];   // bids, refreshes, retries, parked, refresh cycles, (max) busy cycles
     unsigned long long maxbids;
 };
@@ -442,15 +593,40 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
     __shared__ PmLsShared S;
     const int t = threadIdx.x, lane = t & 31;
 
-    for (int j = t; j < ncp; j += blockDim.x) { v[j] = 0.0; owner[j] = PM_LS_NONE; }
+    // state left by the bulk kernel: prices / owners from the cells, free rows (ascending) into the ring
+    __shared__ int s_scan[33];
+    for (int j = t; j < ncp; j += blockDim.x) {
+        const PmLsCell c = V.cell[j];
+        v[j] = (j < nc) ? c.price : 0.0;
+        owner[j] = (j < nc && c.owner != 0xFFFFFFFFu) ? (unsigned short)c.owner : (unsigned short)PM_LS_NONE;
+    }
     for (unsigned q = t; q < B.ring_cap; q += blockDim.x) ring[q] = PM_LS_EMPTY;
     for (int i = t; i < nr; i += blockDim.x) { V.col4row[i] = -1; V.u[i] = 0.0; }
     if (t == 0) {
-        S.fresh = 0; S.head = 0; S.tail = 0; S.maxbids = 0;
+        S.fresh = nr; S.head = 0; S.tail = 0; S.maxbids = 0; S.live = blockDim.x >> 5;
         for (int k = 0; k < 6; ++k) S.stat[k] = 0;
     }
     __syncthreads();
-
+    for (int j = t; j < nc; j += blockDim.x)
+        if (owner[j] != PM_LS_NONE) V.col4row[owner[j]] = j;
+    __syncthreads();
+    for (int base = 0; base < nr; base += blockDim.x) {
+        const int i = base + t;
+        const bool is_free = (i < nr) && (V.col4row[i] < 0);
+        const unsigned bal = __ballot_sync(0xffffffffu, is_free);
+        if (lane == 0) s_scan[t >> 5] = __popc(bal);
+        __syncthreads();
+        if (t == 0) {
+            int acc = (int)S.tail;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { const int c = s_scan[w]; s_scan[w] = acc; acc += c; }
+            s_scan[32] = acc;
+        }
+        __syncthreads();
+        if (is_free) ring[(s_scan[t >> 5] + __popc(bal & ((1u << lane) - 1u))) & ring_mask] = (unsigned short)i;
+        __syncthreads();
+        if (t == 0) S.tail = (unsigned)s_scan[32];
+        __syncthreads();
+    }
     long long bids = 0, refreshes = 0, retries = 0, parked = 0, refresh_cycles = 0;
     const long long t_begin = clock64();
     int carry = -1;          // displaced owner this warp continues with (only when nothing is queued)
@@ -458,6 +634,9 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
         // ---- next row: fresh rows first, then displaced owners in FIFO order
         int row = carry;
         carry = -1;
+        // few chains left: the tail of an epsilon = 0 auction is a sequential price war that one
+        // shortest-augmenting-path search settles at once -> leave the carried row to phase 2
+        if (row >= 0 && *(volatile int *)&S.live <= B.stop_live) break;
         if (row < 0) {
             if (lane == 0) {
                 if (*(volatile int *)&S.fresh < nr) {
@@ -574,6 +753,7 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
         else if (prev != PM_LS_NONE) carry = prev;
     }
     if (lane == 0) {
+        atomicSub(&S.live, 1);
         atomicAdd(&S.stat[0], (unsigned long long)bids);
         atomicAdd(&S.stat[1], (unsigned long long)refreshes);
         atomicAdd(&S.stat[2], (unsigned long long)retries);
@@ -582,6 +762,8 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
         atomicMax(&S.stat[5], (unsigned long long)(clock64() - t_begin));
         atomicMax(&S.maxbids, (unsigned long long)bids);
     }
+    __syncthreads();
+    for (int i = t; i < nr; i += blockDim.x) V.col4row[i] = -1;     // (held the bulk kernel's matching until here)
     __syncthreads();
     // hand the state to phase 2: prices, owners, row duals u_i = c_ij - v_j of the assigned edge
     for (int j = t; j < ncp; j += blockDim.x) {
@@ -598,9 +780,10 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
     if (t == 0) {
         V.counters[3] = (int32_t)(S.maxbids > 0x7fffffffull ? 0x7fffffffull : S.maxbids);
         if (V.stats) {
-            V.stats[PM_LAP_STAT_BIDS] = (long long)S.stat[0];
+            V.stats[PM_LAP_STAT_BIDS] = (long long)S.stat[0] + V.counters[PM_LS_CTR_BIDS];
+            V.stats[PM_LAP_STAT_BULK_BIDS] = V.counters[PM_LS_CTR_BIDS];
             V.stats[PM_LAP_STAT_REFRESHES] = (long long)S.stat[1];
-            V.stats[PM_LAP_STAT_RETRIES] = (long long)S.stat[2];
+            V.stats[PM_LAP_STAT_RETRIES] = (long long)S.stat[2] + V.counters[PM_LS_CTR_RETRIES];
             V.stats[PM_LAP_STAT_PARKED] = (long long)S.stat[3];
             V.stats[PM_LAP_STAT_REFRESH_CYCLES] = (long long)S.stat[4];
             V.stats[PM_LAP_STAT_AUCTION_CYCLES] = (long long)S.stat[5];
@@ -836,6 +1019,19 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
     B.col4row = col4row; B.stats = (long long *)stats; B.total = total;
     // one "round" of the sparse auction = a budget of one bid per row, spread over the 32 warps
     B.max_bids = ((long long)max_bid_rounds * nr + 31) / 32;
+    int bulk_ctas = (nr + 255) / 256;                    // 8 warps per CTA; at most ~2 rows per warp in flight at start
+    if (bulk_ctas > 64) bulk_ctas = 64;
+    {
+        const char *e = getenv("PM_LAP_STOP_LIVE");      // tuning knobs
+        B.stop_live = e ? atoi(e) : 4;
+        e = getenv("PM_LAP_BULK_CTAS");
+        if (e && atoi(e) > 0) bulk_ctas = atoi(e);
+        B.bulk_warps = bulk_ctas * 8;
+        e = getenv("PM_LAP_BULK_STOP");
+        B.bulk_stop_live = e ? atoi(e) : B.bulk_warps / 8;
+        e = getenv("PM_LAP_BULK_PATIENCE");
+        B.bulk_patience = e ? atoi(e) : 50;
+    }
 
     int dev = 0, smem_optin = 0;
     PM_CUDA_TRY(cudaGetDevice(&dev));
@@ -860,6 +1056,8 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
         const int cap = (sms * 8 + batch - 1) / batch;   // ~8 resident CTAs per SM over the whole batch
         if (blocks > cap) blocks = cap;
         pm_ls_build_lists<<<dim3(blocks, batch), 256, 0, s>>>(B);
+        PM_LAUNCH_CHECK();
+        pm_ls_bulk_kernel<<<batch * bulk_ctas, 256, 0, s>>>(B, bulk_ctas);
         PM_LAUNCH_CHECK();
         PM_CUDA_TRY(cudaFuncSetAttribute(pm_ls_auction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem));
         pm_ls_auction_kernel<<<batch, 1024, ls_smem, s>>>(B);
