@@ -14,8 +14,8 @@
 // residual partials.  Three launches per iteration, no host synchronisation inside the loop.
 #include "pm_common.cuh"
 
-#define PM_ICP_PTS 32      // moving points per CTA
-#define PM_ICP_SLICES 8    // column slices per moving point (threads = 32 x 8)
+#define PM_ICP_PTS 16      // moving points per CTA
+#define PM_ICP_SLICES 16   // column slices per moving point (threads = 16 x 16)
 #define PM_ICP_TILE 512    // fixed points staged per tile
 #define PM_ICP_NSUM 22     // 10 (M M^T upper) + 12 (F M^T)
 
@@ -28,22 +28,29 @@ pm_icp_nn_kernel(const double *__restrict__ cur, int n1, const double *__restric
     __shared__ double best_d[PM_ICP_SLICES][PM_ICP_PTS];
     __shared__ int best_j[PM_ICP_SLICES][PM_ICP_PTS];
     __shared__ double sums[PM_ICP_PTS][PM_ICP_NSUM + 1];
-    const int p = threadIdx.x & 31, s = threadIdx.x >> 5;
+    const int p = threadIdx.x % PM_ICP_PTS, s = threadIdx.x / PM_ICP_PTS;
     const int i = blockIdx.x * PM_ICP_PTS + p;
     const bool live = i < n1;
     double mx = 0, my = 0, mz = 0;
     if (live) { mx = cur[3 * i]; my = cur[3 * i + 1]; mz = cur[3 * i + 2]; }
-    double bd = INFINITY;
+    // The reference keeps the first strict minimum of sqrt(d2) in ascending j.  sqrt is monotone, so a new
+    // minimum needs d2 < best d2: the hot loop compares squared distances and only on that (rare) branch
+    // evaluates the square roots, which decide exactly like the reference (two different d2 can round to
+    // the same distance, and then the earlier index must stay).
+    double bd = INFINITY, bd2 = INFINITY;
     int bj = 0x7fffffff;
     for (int t0 = 0; t0 < n2; t0 += PM_ICP_TILE) {
         const int tn = min(PM_ICP_TILE, n2 - t0);
         __syncthreads();
         for (int q = threadIdx.x; q < tn * 3; q += blockDim.x) tile[q] = fixed[(size_t)t0 * 3 + q];
         __syncthreads();
-        for (int j = s; j < tn; j += PM_ICP_SLICES) {   // all lanes of a warp read the same tile entry
+        for (int j = s; j < tn; j += PM_ICP_SLICES) {   // lanes of one slice read the same tile entry (broadcast)
             const double d0 = tile[3 * j] - mx, d1 = tile[3 * j + 1] - my, d2 = tile[3 * j + 2] - mz;
-            const double d = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2)));
-            if (d < bd) { bd = d; bj = t0 + j; }          // ascending j within a slice: first min kept
+            const double q2 = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+            if (q2 < bd2) {                               // ascending j within a slice: first min kept
+                const double d = sqrt(q2);
+                if (d < bd) { bd = d; bd2 = q2; bj = t0 + j; }
+            }
         }
     }
     best_d[s][p] = bd;
