@@ -122,7 +122,7 @@ int pm_chi2_cost(const float *a_t, int lda, const uint32_t *a_mask, int n1, cons
  *   total    [batch] float64 out: sum of assigned costs
  *   stats    [batch][PM_LAP_STATS] int64 out, may be NULL (see PM_LAP_STAT_*)
  * workspace: pm_lap_workspace_bytes(batch, nr, nc). */
-#define PM_LAP_STATS 12
+#define PM_LAP_STATS 16
 #define PM_LAP_STAT_BID_ROUNDS 0 /* dense: rounds run; sparse: largest number of bids made by one warp */
 #define PM_LAP_STAT_ROWS_AFTER_BIDDING 1
 #define PM_LAP_STAT_AUGMENTATIONS 2
@@ -135,6 +135,7 @@ int pm_chi2_cost(const float *a_t, int lda, const uint32_t *a_mask, int n1, cons
 #define PM_LAP_STAT_REFRESH_CYCLES 9  /* sparse auction: SM cycles spent rebuilding lists, summed over warps */
 #define PM_LAP_STAT_AUCTION_CYCLES 10 /* sparse auction: SM cycles of the longest-running warp */
 #define PM_LAP_STAT_BULK_BIDS 11      /* sparse auction: bids made by the multi-SM bulk kernel */
+#define PM_LAP_STAT_SAP_DENSE_RELAX 12 /* sparse augmenting paths: tree rows that had to be relaxed densely */
 #define PM_LAP_ALGO_AUTO 0
 #define PM_LAP_ALGO_SPARSE_AUCTION 1
 #define PM_LAP_ALGO_DENSE_AUCTION 2

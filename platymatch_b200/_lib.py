@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libplatymatch_b200.so")
 
 NBINS = 360
-LAP_STATS = 12
+LAP_STATS = 16
 CHI2_EPS = 2.0 ** -60
 CHI2_TILE = 128
 

@@ -972,6 +972,199 @@ __global__ void __launch_bounds__(PM_LAP_MAX_THREADS, 1) pm_lap_sap_kernel(PmLap
     (void)final_parity;
 }
 
+// ------------------------------------------------------------------------------------- phase 2 (sparse)
+// Shortest augmenting paths over the certified candidate lists of the auction.  A Dijkstra step adds
+// one row to the alternating tree; instead of the row's 8000 dense costs (one HBM round trip) it
+// relaxes the <= 128 list edges (L2).  The certificate (*) of the lists bounds what that leaves out:
+// every edge of tree row i outside its list has reduced cost >= tau_i - u_i, so no path through such
+// an edge is shorter than bound_i = D_i + tau_i - u_i.  A column is finalised only while its distance
+// is <= the smallest bound over the tree; otherwise the row holding that bound is relaxed densely
+// (exactly the dense algorithm's step) and its bound removed.  Same result as the dense search.
+//
+// dynamic shared memory: v f64[ncp] | d f64[ncp] | pred u16[ncp] | r4c u16[ncp] | scanned u8[ncp]
+#define PM_SS_THREADS 1024
+
+__global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmLapBatch B) {
+    extern __shared__ __align__(16) unsigned char pm_ss_smem[];
+    const PmLapView V = pm_lap_view(B, blockIdx.x);
+    const int nc = B.nc, nr = B.nr, ncp = B.ncp, ldc = B.ldc;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    double *v = reinterpret_cast<double *>(pm_ss_smem);
+    double *d = v + ncp;
+    unsigned short *pred = reinterpret_cast<unsigned short *>(d + ncp);
+    unsigned short *r4c = pred + ncp;
+    unsigned char *scanned = reinterpret_cast<unsigned char *>(r4c + ncp);
+    __shared__ double s_val[2][32];
+    __shared__ int s_tie[2][32];
+    __shared__ int s_scan[33];
+    __shared__ int s_nfree;
+    __shared__ double s_lam;
+    __shared__ int s_lam_idx;
+    int32_t *tree_row = V.bid_col;                 // [nr] scratch of the dense auction, free here
+    double *tree_dist = V.bid_gamma;               // [nr]
+    double *tree_bound = reinterpret_cast<double *>(V.colbest);   // [nc] >= [nr]
+
+    for (int j = t; j < ncp; j += PM_SS_THREADS) {
+        const int r = (j < nc) ? V.row4col[j] : -1;
+        v[j] = (j < nc) ? V.v[j] : 0.0;
+        r4c[j] = (r < 0) ? (unsigned short)PM_LS_NONE : (unsigned short)r;
+    }
+    // ordered list of free rows (ascending row index) into free_lists
+    int32_t *flist = V.free_lists;
+    if (t == 0) s_nfree = 0;
+    __syncthreads();
+    for (int base = 0; base < nr; base += PM_SS_THREADS) {
+        const int i = base + t;
+        const bool is_free = (i < nr) && (V.col4row[i] < 0);
+        const unsigned bal = __ballot_sync(0xffffffffu, is_free);
+        if (lane == 0) s_scan[warp] = __popc(bal);
+        __syncthreads();
+        if (t == 0) {
+            int acc = s_nfree;
+            for (int w = 0; w < 32; ++w) { const int c = s_scan[w]; s_scan[w] = acc; acc += c; }
+            s_scan[32] = acc;
+        }
+        __syncthreads();
+        if (is_free) flist[s_scan[warp] + __popc(bal & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (t == 0) s_nfree = s_scan[32];
+        __syncthreads();
+    }
+    const int nfree = s_nfree;
+    long long steps = 0, dense_relax = 0;
+    int status = 0, parity = 0;
+
+    for (int f = 0; f < nfree && status == 0; ++f) {
+        const int cur = flist[f];
+        for (int j = t; j < ncp; j += PM_SS_THREADS) { d[j] = INFINITY; scanned[j] = 0; }
+        if (t == 0) { s_lam = INFINITY; s_lam_idx = -1; }
+        __syncthreads();
+        int i = cur, sink = -1, nt = 0;
+        double dist = 0.0, min_val = 0.0;
+        while (sink < 0 && status == 0) {
+            // ---- add row i (distance dist) to the tree: relax its list edges, record its bound
+            const double ui = __ldcg(V.u + i);
+            if (t < PM_LS_K) {
+                const int j = __ldcg(V.lcol + (size_t)i * PM_LS_K + t);
+                if (j >= 0 && !scanned[j]) {
+                    const double r = ((dist + (double)__ldcg(V.lcost + (size_t)i * PM_LS_K + t)) - ui) - v[j];
+                    if (r < d[j]) { d[j] = r; pred[j] = (unsigned short)i; }
+                }
+            } else if (t == PM_LS_K) {
+                const double bound = (dist + __ldcg(V.tau + i)) - ui;
+                tree_row[nt] = i; tree_dist[nt] = dist; tree_bound[nt] = bound;
+                if (bound < s_lam) { s_lam = bound; s_lam_idx = nt; }
+            }
+            ++nt;
+            __syncthreads();
+            while (true) {
+                // ---- closest unscanned column (ties prefer a free column, then the lower index)
+                double best = INFINITY;
+                int best_tie = INT_MAX;
+                for (int j = t; j < nc; j += PM_SS_THREADS) {
+                    if (!scanned[j]) {
+                        const double dj = d[j];
+                        const int tie = ((r4c[j] != PM_LS_NONE) ? (1 << 30) : 0) | j;
+                        if (dj < best || (dj == best && tie < best_tie)) { best = dj; best_tie = tie; }
+                    }
+                }
+                pm_argmin_warp(best, best_tie);
+                if (lane == 0) { s_val[parity][warp] = best; s_tie[parity][warp] = best_tie; }
+                __syncthreads();
+                best = s_val[parity][lane];
+                best_tie = s_tie[parity][lane];
+                pm_argmin_warp(best, best_tie);
+                parity ^= 1;
+                const double lam = s_lam;
+                const int lam_idx = s_lam_idx;
+                if (best <= lam) {
+                    if (!(best < INFINITY)) { status = PM_ERR_INFEASIBLE; break; }
+                    ++steps;
+                    min_val = best;
+                    const int jm = best_tie & ((1 << 30) - 1);
+                    if (t == 0) scanned[jm] = 1;
+                    if (!(best_tie >> 30)) sink = jm;
+                    else { i = r4c[jm]; dist = best; }
+                    __syncthreads();                           // the scanned flag is visible before the next relaxation
+                    break;
+                }
+                // ---- an edge outside the list of tree row `il` could be shorter: relax that row densely
+                __syncthreads();                               // everybody has read s_lam
+                const int il = tree_row[lam_idx];
+                const double dl = tree_dist[lam_idx], uil = __ldcg(V.u + il);
+                const float *ci = V.cost + (size_t)il * ldc;
+                for (int j = t; j < nc; j += PM_SS_THREADS) {
+                    if (!scanned[j]) {
+                        const double r = ((dl + (double)ci[j]) - uil) - v[j];
+                        if (r < d[j]) { d[j] = r; pred[j] = (unsigned short)il; }
+                    }
+                }
+                ++dense_relax;
+                if (t == 0) tree_bound[lam_idx] = INFINITY;
+                __syncthreads();
+                if (warp == 0) {                               // smallest remaining bound over the tree
+                    double lb = INFINITY;
+                    int li = INT_MAX;
+                    for (int k = lane; k < nt; k += 32) {
+                        const double bnd = tree_bound[k];
+                        if (bnd < lb || (bnd == lb && k < li)) { lb = bnd; li = k; }
+                    }
+                    pm_argmin_warp(lb, li);
+                    if (lane == 0) { s_lam = lb; s_lam_idx = (lb < INFINITY) ? li : -1; }
+                }
+                __syncthreads();
+            }
+        }
+        if (status) break;
+        __syncthreads();
+        // dual update (Crouse: u[cur] += min; scanned rows / columns shift by min - d); prices only fall
+        for (int j = t; j < nc; j += PM_SS_THREADS) {
+            if (scanned[j]) {
+                const double delta = min_val - d[j];
+                v[j] -= delta;
+                if (j != sink) V.u[r4c[j]] += delta;
+            }
+        }
+        if (t == 0) V.u[cur] += min_val;
+        __syncthreads();
+        if (t == 0) {   // augment along the predecessor chain
+            int j = sink;
+            while (true) {
+                const int r = pred[j];
+                r4c[j] = (unsigned short)r;
+                const int jn = V.col4row[r];
+                V.col4row[r] = j;
+                j = jn;
+                if (r == cur) break;
+            }
+        }
+        __syncthreads();
+    }
+    for (int j = t; j < nc; j += PM_SS_THREADS) {
+        V.v[j] = v[j];
+        V.row4col[j] = (r4c[j] == PM_LS_NONE) ? -1 : (int)r4c[j];
+    }
+    __syncthreads();
+    double tot = 0.0;
+    for (int r = t; r < nr; r += PM_SS_THREADS) {
+        const int c = V.col4row[r];
+        if (c >= 0) tot += (double)V.cost[(size_t)r * ldc + c];
+    }
+    tot = pm_block_sum(tot, &s_val[0][0]);
+    if (t == 0) {
+        V.total[0] = status ? nan("") : tot;
+        V.counters[4] = status;
+        if (V.stats) {
+            V.stats[PM_LAP_STAT_BID_ROUNDS] = V.counters[3];
+            V.stats[PM_LAP_STAT_ROWS_AFTER_BIDDING] = nr - nfree;
+            V.stats[PM_LAP_STAT_AUGMENTATIONS] = nfree;
+            V.stats[PM_LAP_STAT_DIJKSTRA_STEPS] = steps;
+            V.stats[PM_LAP_STAT_STATUS] = status;
+            V.stats[PM_LAP_STAT_SAP_DENSE_RELAX] = dense_relax;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------- host
 extern "C" size_t pm_lap_workspace_bytes(int batch, int nr, int nc) {
     if (batch < 1 || nr < 1 || nc < 1) return 0;
@@ -1075,7 +1268,14 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
         PM_LAUNCH_CHECK();
     }
     int rc;
-    if (nc <= PM_LAP_CPT * PM_LAP_MAX_THREADS) {
+    const size_t ss_smem = (size_t)B.ncp * (8 + 8 + 2 + 2 + 1);
+    if (max_bid_rounds > 0 && algorithm == PM_LAP_ALGO_SPARSE_AUCTION && ss_smem + 2048 <= (size_t)smem_optin &&
+        !getenv("PM_LAP_DENSE_SAP")) {
+        PM_CUDA_TRY(cudaFuncSetAttribute(pm_lap_sap_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss_smem));
+        pm_lap_sap_sparse_kernel<<<batch, PM_SS_THREADS, ss_smem, s>>>(B);
+        PM_LAUNCH_CHECK();
+        rc = PM_OK;
+    } else if (nc <= PM_LAP_CPT * PM_LAP_MAX_THREADS) {
         int threads = ((nc + PM_LAP_CPT - 1) / PM_LAP_CPT + 31) & ~31;
         if (threads < 64) threads = 64;
         if (threads > PM_LAP_MAX_THREADS) threads = PM_LAP_MAX_THREADS;

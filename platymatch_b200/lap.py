@@ -45,5 +45,6 @@ def linear_sum_assignment(cost_matrix, maximize=False, return_stats=False, max_b
         return rows, col, dict(total=float(total.item()), bid_rounds=int(st[0]), rows_after_bidding=int(st[1]),
                                augmentations=int(st[2]), dijkstra_steps=int(st[3]), bids=int(st[5]),
                                refreshes=int(st[6]), retries=int(st[7]), parked=int(st[8]),
-                               refresh_cycles=int(st[9]), auction_cycles=int(st[10]))
+                               refresh_cycles=int(st[9]), auction_cycles=int(st[10]), bulk_bids=int(st[11]),
+                               sap_dense_relax=int(st[12]))
     return rows, col

@@ -16,7 +16,7 @@ cost = torch.empty((4, n1, (n2 + 3) // 4 * 4), dtype=torch.float32, device="cuda
 for q, (a, b) in enumerate(P.HYPOTHESES_DISTINCT):
     D.chi2_cost(dm.operand(a), df.operand(b), out=cost[q])
 names = ["bid_rounds", "rows_after", "augment", "dijkstra", "status", "bids", "refreshes", "retries", "parked",
-         "refresh_cyc", "auction_cyc", "-"]
+         "refresh_cyc", "auction_cyc", "bulk_bids", "sap_dense", "-", "-", "-"]
 for batch in ([0], [1], [2], [3], [0, 1, 2, 3]):
     c = cost[batch].contiguous()
     for rep in range(3):
