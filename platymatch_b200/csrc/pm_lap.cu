@@ -68,6 +68,7 @@ static inline size_t pm_lap_align(size_t x) { return (x + 255) & ~(size_t)255; }
 #define PM_LS_CTR_BIDS 9
 #define PM_LS_CTR_RETRIES 10
 #define PM_LS_CTR_DROPPED 11
+#define PM_LS_CTR_REFRESHES 12
 
 struct PmLapLayout {
     size_t u, v, row4col, bid_col, bid_gamma, colbest, free_lists, counters, lcol, lcost, tau, width, ring, ring32, cell, per_item;
@@ -402,6 +403,9 @@ __device__ __forceinline__ unsigned long long pm_warp_min_u64(unsigned long long
 // Rebuild the list of one row at current prices (one warp): every column with c - v < limit goes into
 // the row's 128 slots in column order; what does not fit lowers tau.  Returns the number of entries
 // (uniform); the lane's own slots and the new tau / width come back in registers.
+// CELLS: prices are the first double of the bulk kernel's 16-byte global cells (read through L2);
+// otherwise a plain (shared-memory) array.  A stale price only makes the certificate more conservative.
+template <bool CELLS>
 __device__ __forceinline__ int pm_ls_refresh_row(const PmLapView &V, int row, const float *__restrict__ ci,
                                                  const double *v, int nc, int lane, double limit, int4 &cj,
                                                  float4 &cc, double &tau, double &wmin_out) {
@@ -427,7 +431,8 @@ __device__ __forceinline__ int pm_ls_refresh_row(const PmLapView &V, int row, co
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int j = j0 + e;
-                w[e] = (j < nc) ? (double)cs[e] - v[j] : INFINITY;
+                w[e] = INFINITY;
+                if (j < nc) w[e] = (double)cs[e] - (CELLS ? __ldcg(v + 2 * (size_t)j) : v[j]);
                 wmin = fmin(wmin, w[e]);
             }
             const bool any = (w[0] < limit) || (w[1] < limit) || (w[2] < limit) || (w[3] < limit);
@@ -488,44 +493,54 @@ __device__ __forceinline__ bool pm_ls_cas128(PmLsCell *addr, double exp_price, u
 
 __global__ void __launch_bounds__(256) pm_ls_bulk_kernel(PmLapBatch B, int ctas_per_matrix) {
     const PmLapView V = pm_lap_view(B, blockIdx.x / ctas_per_matrix);
-    const int nr = B.nr, lane = threadIdx.x & 31;
+    const int nr = B.nr, nc = B.nc, lane = threadIdx.x & 31;
     PmLsCell *cell = V.cell;
     volatile unsigned *ring = V.ring32;
     const unsigned ring_mask = B.ring_cap - 1;
     volatile int *ctr = V.counters;
-    int bids = 0, retries = 0, dropped = 0;
+    int bids = 0, retries = 0, dropped = 0, refreshes = 0;
+    int carry = -1;
     while (bids < B.max_bids) {
-        int row = -1;
-        if (lane == 0) {
-            if (ctr[PM_LS_CTR_FRESH] < nr) {
-                const int r = atomicAdd(&V.counters[PM_LS_CTR_FRESH], 1);
-                if (r < nr) row = r;
-            }
-            if (row < 0 && ctr[PM_LS_CTR_LIVE] > B.bulk_stop_live) {
-                // ticket pop: slots fill in ticket order; a warp that waits too long for its slot leaves (the
-                // parallelism has collapsed) - a row that later lands in an abandoned slot simply stays free
-                const unsigned ticket = atomicAdd((unsigned *)&V.counters[PM_LS_CTR_HEAD], 1u);
-                for (int spin = 0; spin < B.bulk_patience; ++spin) {
-                    const unsigned x = ring[ticket & ring_mask];
-                    if (x != 0xFFFFFFFFu) { ring[ticket & ring_mask] = 0xFFFFFFFFu; row = (int)x; break; }
-                    if (ctr[PM_LS_CTR_LIVE] <= B.bulk_stop_live) break;
-                    __nanosleep(200);
+        int row = carry;
+        carry = -1;
+        if (row >= 0 && ctr[PM_LS_CTR_LIVE] <= B.bulk_stop_live) break;    // few chains left: tail kernel
+        if (row < 0) {
+            if (lane == 0) {
+                if (ctr[PM_LS_CTR_FRESH] < nr) {
+                    const int r = atomicAdd(&V.counters[PM_LS_CTR_FRESH], 1);
+                    if (r < nr) row = r;
+                }
+                if (row < 0 && ctr[PM_LS_CTR_LIVE] > B.bulk_stop_live &&
+                    (int)((unsigned)ctr[PM_LS_CTR_TAIL] - (unsigned)ctr[PM_LS_CTR_HEAD]) > 0) {
+                    // ticket pop: slots fill in ticket order; a warp whose ticket overshot the queue waits a
+                    // little for the next push and then leaves - a row that later lands in an abandoned
+                    // slot simply stays free for the tail kernel
+                    const unsigned ticket = atomicAdd((unsigned *)&V.counters[PM_LS_CTR_HEAD], 1u);
+                    for (int spin = 0; spin < B.bulk_patience; ++spin) {
+                        const unsigned x = ring[ticket & ring_mask];
+                        if (x != 0xFFFFFFFFu) { ring[ticket & ring_mask] = 0xFFFFFFFFu; row = (int)x; break; }
+                        if (ctr[PM_LS_CTR_LIVE] <= B.bulk_stop_live) break;
+                        __nanosleep(200);
+                    }
                 }
             }
+            row = __shfl_sync(0xffffffffu, row, 0);
+            if (row < 0) break;
         }
-        row = __shfl_sync(0xffffffffu, row, 0);
-        if (row < 0) break;
-        const int4 cj = __ldcg(reinterpret_cast<const int4 *>(V.lcol + (size_t)row * PM_LS_K) + lane);
-        const float4 cc = __ldcg(reinterpret_cast<const float4 *>(V.lcost + (size_t)row * PM_LS_K) + lane);
-        const double tau = __ldcg(V.tau + row);
-        const int js[4] = {cj.x, cj.y, cj.z, cj.w};
-        const float cs[4] = {cc.x, cc.y, cc.z, cc.w};
-        bool won = false;
+        int4 cj = __ldcg(reinterpret_cast<const int4 *>(V.lcol + (size_t)row * PM_LS_K) + lane);
+        float4 cc = __ldcg(reinterpret_cast<const float4 *>(V.lcost + (size_t)row * PM_LS_K) + lane);
+        double tau = __ldcg(V.tau + row);
+        bool fresh = false, won = false;
         while (true) {
+            const int js[4] = {cj.x, cj.y, cj.z, cj.w};
+            const float cs[4] = {cc.x, cc.y, cc.z, cc.w};
             double vs[4], ws[4];
+            unsigned os[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                vs[e] = *reinterpret_cast<volatile double *>(&cell[js[e] < 0 ? 0 : js[e]].price);
+            for (int e = 0; e < 4; ++e) {       // {price, owner} of the cell in one 16-byte load
+                const ulonglong2 c = __ldcv(reinterpret_cast<const ulonglong2 *>(&cell[js[e] < 0 ? 0 : js[e]]));
+                vs[e] = __longlong_as_double((long long)c.x);
+                os[e] = (unsigned)c.y;
                 const double w = (double)cs[e] - vs[e];
                 ws[e] = js[e] < 0 ? INFINITY : w;
             }
@@ -539,26 +554,53 @@ __global__ void __launch_bounds__(256) pm_ls_bulk_kernel(PmLapBatch B, int ctas_
             const bool holder = lane == hl;
             const double bw = pm_ordval(kb);
             const double sw = pm_ordval(pm_warp_min_u64(pm_ordkey(holder ? w2 : w1)));
-            if (!(bw < tau)) break;                         // list exhausted (or no finite entry): tail kernel
+            if (!(bw < INFINITY)) break;                    // no finite entry: phase 2 reports it
+            if (!(bw < tau) && !(fresh && bw <= tau)) {     // list exhausted: rebuild from the dense row
+                double width = __ldcg(V.width + row), wmin;
+                if (!(width > 0.0) || !(width < INFINITY)) width = fabs(tau) * 1e-3 + 1e-300;
+                const float *ci = V.cost + (size_t)row * B.ldc;
+                const double *prices = reinterpret_cast<const double *>(cell);
+                int n = pm_ls_refresh_row<true>(V, row, ci, prices, nc, lane, tau + width, cj, cc, tau, wmin);
+                if (n < 8 && wmin < INFINITY) {
+                    width *= 4.0;
+                    n = pm_ls_refresh_row<true>(V, row, ci, prices, nc, lane, wmin + width, cj, cc, tau, wmin);
+                } else if (n >= PM_LS_K) {
+                    width *= 0.5;
+                }
+                if (lane == 0) { V.tau[row] = tau; V.width[row] = width; }
+                __threadfence();                            // the next warp that serves this row may sit on another SM
+                fresh = true;
+                ++refreshes;
+                continue;
+            }
             double gamma = fmin(sw, tau) - bw;
             if (!(gamma > 0.0)) gamma = 0.0;
             int result = PM_LS_RETRY;
+            unsigned prev = 0xFFFFFFFFu;
             if (holder) {
                 const bool m0 = ws[0] == w1, m1 = ws[1] == w1, m2 = ws[2] == w1;
                 const int bj = m0 ? js[0] : m1 ? js[1] : m2 ? js[2] : js[3];
                 const double v1 = m0 ? vs[0] : m1 ? vs[1] : m2 ? vs[2] : vs[3];
-                const unsigned own = *reinterpret_cast<volatile unsigned *>(&cell[bj].owner);
+                const unsigned own = m0 ? os[0] : m1 ? os[1] : m2 ? os[2] : os[3];
                 if (gamma == 0.0 && own != 0xFFFFFFFFu) result = PM_LS_PARK;            // zero-increment steal
                 else if (pm_ls_cas128(&cell[bj], v1, own, v1 - gamma, (unsigned)row)) {
                     result = PM_LS_WON;
-                    if (own != 0xFFFFFFFFu) {                                           // displaced owner: queue it
-                        const unsigned pos = atomicAdd((unsigned *)&V.counters[PM_LS_CTR_TAIL], 1u);
-                        ring[pos & ring_mask] = own;
+                    if (own != 0xFFFFFFFFu) {
+                        // displaced owner: behind everything that is queued, or carried on by this warp
+                        const bool queued = ctr[PM_LS_CTR_FRESH] < nr ||
+                                            (int)((unsigned)ctr[PM_LS_CTR_TAIL] - (unsigned)ctr[PM_LS_CTR_HEAD]) > 0;
+                        if (queued) {
+                            const unsigned pos = atomicAdd((unsigned *)&V.counters[PM_LS_CTR_TAIL], 1u);
+                            ring[pos & ring_mask] = own;
+                        } else {
+                            prev = own;
+                        }
                     }
                 }
             }
             result = __shfl_sync(0xffffffffu, result, hl);
-            if (result == PM_LS_WON) { won = true; break; }
+            prev = __shfl_sync(0xffffffffu, prev, hl);
+            if (result == PM_LS_WON) { won = true; if (prev != 0xFFFFFFFFu) carry = (int)prev; break; }
             if (result == PM_LS_PARK) break;
             ++retries;
         }
@@ -570,6 +612,7 @@ __global__ void __launch_bounds__(256) pm_ls_bulk_kernel(PmLapBatch B, int ctas_
         atomicAdd(&V.counters[PM_LS_CTR_BIDS], bids);
         atomicAdd(&V.counters[PM_LS_CTR_RETRIES], retries);
         atomicAdd(&V.counters[PM_LS_CTR_DROPPED], dropped);
+        atomicAdd(&V.counters[PM_LS_CTR_REFRESHES], refreshes);
     }
 }
 
@@ -692,10 +735,10 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
                 const long long t0 = clock64();
                 double width = __ldcg(V.width + row), wmin;
                 if (!(width > 0.0) || !(width < INFINITY)) width = fabs(tau) * 1e-3 + 1e-300;
-                int n = pm_ls_refresh_row(V, row, V.cost + (size_t)row * B.ldc, v, nc, lane, tau + width, cj, cc, tau, wmin);
+                int n = pm_ls_refresh_row<false>(V, row, V.cost + (size_t)row * B.ldc, v, nc, lane, tau + width, cj, cc, tau, wmin);
                 if (n < 8 && wmin < INFINITY) {        // window too narrow (prices moved a lot): centre it on the minimum
                     width *= 4.0;
-                    n = pm_ls_refresh_row(V, row, V.cost + (size_t)row * B.ldc, v, nc, lane, wmin + width, cj, cc, tau, wmin);
+                    n = pm_ls_refresh_row<false>(V, row, V.cost + (size_t)row * B.ldc, v, nc, lane, wmin + width, cj, cc, tau, wmin);
                 } else if (n >= PM_LS_K) {
                     width *= 0.5;
                 }
@@ -782,7 +825,7 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
         if (V.stats) {
             V.stats[PM_LAP_STAT_BIDS] = (long long)S.stat[0] + V.counters[PM_LS_CTR_BIDS];
             V.stats[PM_LAP_STAT_BULK_BIDS] = V.counters[PM_LS_CTR_BIDS];
-            V.stats[PM_LAP_STAT_REFRESHES] = (long long)S.stat[1];
+            V.stats[PM_LAP_STAT_REFRESHES] = (long long)S.stat[1] + V.counters[PM_LS_CTR_REFRESHES];
             V.stats[PM_LAP_STAT_RETRIES] = (long long)S.stat[2] + V.counters[PM_LS_CTR_RETRIES];
             V.stats[PM_LAP_STAT_PARKED] = (long long)S.stat[3];
             V.stats[PM_LAP_STAT_REFRESH_CYCLES] = (long long)S.stat[4];
@@ -981,7 +1024,7 @@ __global__ void __launch_bounds__(PM_LAP_MAX_THREADS, 1) pm_lap_sap_kernel(PmLap
 // is <= the smallest bound over the tree; otherwise the row holding that bound is relaxed densely
 // (exactly the dense algorithm's step) and its bound removed.  Same result as the dense search.
 //
-// dynamic shared memory: v f64[ncp] | d f64[ncp] | pred u16[ncp] | r4c u16[ncp] | scanned u8[ncp]
+// dynamic shared memory: v f64[ncp] | d f64[ncp] | pred u16[ncp] | r4c u16[ncp] | front u16[ncp] | scanned u8[ncp]
 #define PM_SS_THREADS 1024
 
 __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmLapBatch B) {
@@ -993,7 +1036,9 @@ __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmL
     double *d = v + ncp;
     unsigned short *pred = reinterpret_cast<unsigned short *>(d + ncp);
     unsigned short *r4c = pred + ncp;
-    unsigned char *scanned = reinterpret_cast<unsigned char *>(r4c + ncp);
+    unsigned short *front = r4c + ncp;             // columns reached so far in this search (finite distance)
+    unsigned char *scanned = reinterpret_cast<unsigned char *>(front + ncp);
+    __shared__ int s_nfront;
     __shared__ double s_val[2][32];
     __shared__ int s_tie[2][32];
     __shared__ int s_scan[33];
@@ -1037,7 +1082,7 @@ __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmL
     for (int f = 0; f < nfree && status == 0; ++f) {
         const int cur = flist[f];
         for (int j = t; j < ncp; j += PM_SS_THREADS) { d[j] = INFINITY; scanned[j] = 0; }
-        if (t == 0) { s_lam = INFINITY; s_lam_idx = -1; }
+        if (t == 0) { s_lam = INFINITY; s_lam_idx = -1; s_nfront = 0; }
         __syncthreads();
         int i = cur, sink = -1, nt = 0;
         double dist = 0.0, min_val = 0.0;
@@ -1048,7 +1093,11 @@ __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmL
                 const int j = __ldcg(V.lcol + (size_t)i * PM_LS_K + t);
                 if (j >= 0 && !scanned[j]) {
                     const double r = ((dist + (double)__ldcg(V.lcost + (size_t)i * PM_LS_K + t)) - ui) - v[j];
-                    if (r < d[j]) { d[j] = r; pred[j] = (unsigned short)i; }
+                    const double old = d[j];
+                    if (r < old) {
+                        if (!(old < INFINITY)) front[atomicAdd(&s_nfront, 1)] = (unsigned short)j;   // first time reached
+                        d[j] = r; pred[j] = (unsigned short)i;
+                    }
                 }
             } else if (t == PM_LS_K) {
                 const double bound = (dist + __ldcg(V.tau + i)) - ui;
@@ -1061,7 +1110,9 @@ __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmL
                 // ---- closest unscanned column (ties prefer a free column, then the lower index)
                 double best = INFINITY;
                 int best_tie = INT_MAX;
-                for (int j = t; j < nc; j += PM_SS_THREADS) {
+                const int nfront = s_nfront;
+                for (int q = t; q < nfront; q += PM_SS_THREADS) {
+                    const int j = front[q];
                     if (!scanned[j]) {
                         const double dj = d[j];
                         const int tie = ((r4c[j] != PM_LS_NONE) ? (1 << 30) : 0) | j;
@@ -1096,7 +1147,11 @@ __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmL
                 for (int j = t; j < nc; j += PM_SS_THREADS) {
                     if (!scanned[j]) {
                         const double r = ((dl + (double)ci[j]) - uil) - v[j];
-                        if (r < d[j]) { d[j] = r; pred[j] = (unsigned short)il; }
+                        const double old = d[j];
+                        if (r < old) {
+                            if (!(old < INFINITY)) front[atomicAdd(&s_nfront, 1)] = (unsigned short)j;
+                            d[j] = r; pred[j] = (unsigned short)il;
+                        }
                     }
                 }
                 ++dense_relax;
@@ -1221,7 +1276,7 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
         if (e && atoi(e) > 0) bulk_ctas = atoi(e);
         B.bulk_warps = bulk_ctas * 8;
         e = getenv("PM_LAP_BULK_STOP");
-        B.bulk_stop_live = e ? atoi(e) : B.bulk_warps / 8;
+        B.bulk_stop_live = e ? atoi(e) : 12;
         e = getenv("PM_LAP_BULK_PATIENCE");
         B.bulk_patience = e ? atoi(e) : 50;
     }
@@ -1268,7 +1323,7 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
         PM_LAUNCH_CHECK();
     }
     int rc;
-    const size_t ss_smem = (size_t)B.ncp * (8 + 8 + 2 + 2 + 1);
+    const size_t ss_smem = (size_t)B.ncp * (8 + 8 + 2 + 2 + 2 + 1);
     if (max_bid_rounds > 0 && algorithm == PM_LAP_ALGO_SPARSE_AUCTION && ss_smem + 2048 <= (size_t)smem_optin &&
         !getenv("PM_LAP_DENSE_SAP")) {
         PM_CUDA_TRY(cudaFuncSetAttribute(pm_lap_sap_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss_smem));
