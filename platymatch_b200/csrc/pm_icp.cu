@@ -24,7 +24,7 @@
 __global__ void __launch_bounds__(PM_ICP_PTS * PM_ICP_SLICES)
 pm_icp_nn_kernel(const double *__restrict__ cur, int n1, const double *__restrict__ fixed, int n2,
                  const double *__restrict__ shift, int32_t *__restrict__ nn, double *__restrict__ partial) {
-    __shared__ double tile[PM_ICP_TILE * 3];
+    __shared__ __align__(16) double tile[2][PM_ICP_TILE * 3];      // double-buffered with cp.async
     __shared__ double best_d[PM_ICP_SLICES][PM_ICP_PTS];
     __shared__ int best_j[PM_ICP_SLICES][PM_ICP_PTS];
     __shared__ double sums[PM_ICP_PTS][PM_ICP_NSUM + 1];
@@ -39,19 +39,51 @@ pm_icp_nn_kernel(const double *__restrict__ cur, int n1, const double *__restric
     // the same distance, and then the earlier index must stay).
     double bd = INFINITY, bd2 = INFINITY;
     int bj = 0x7fffffff;
-    for (int t0 = 0; t0 < n2; t0 += PM_ICP_TILE) {
+    auto stage = [&](int buf, int t0) {        // 8-byte cp.async copies of one tile of the fixed cloud
         const int tn = min(PM_ICP_TILE, n2 - t0);
+        for (int q = threadIdx.x; q < tn * 3; q += blockDim.x) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&tile[buf][q]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(fixed + (size_t)t0 * 3 + q));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    stage(0, 0);
+    int buf = 0;
+    for (int t0 = 0; t0 < n2; t0 += PM_ICP_TILE, buf ^= 1) {
+        const int tn = min(PM_ICP_TILE, n2 - t0);
+        if (t0 + PM_ICP_TILE < n2) {
+            stage(buf ^ 1, t0 + PM_ICP_TILE);
+            asm volatile("cp.async.wait_group 1;");
+        } else {
+            asm volatile("cp.async.wait_group 0;");
+        }
         __syncthreads();
-        for (int q = threadIdx.x; q < tn * 3; q += blockDim.x) tile[q] = fixed[(size_t)t0 * 3 + q];
-        __syncthreads();
-        for (int j = s; j < tn; j += PM_ICP_SLICES) {   // lanes of one slice read the same tile entry (broadcast)
-            const double d0 = tile[3 * j] - mx, d1 = tile[3 * j + 1] - my, d2 = tile[3 * j + 2] - mz;
+        const double *tl = tile[buf];
+        int j = s;
+        for (; j + PM_ICP_SLICES < tn; j += 2 * PM_ICP_SLICES) {   // two candidates per trip: independent chains
+            const int ja = j, jb = j + PM_ICP_SLICES;
+            const double a0 = tl[3 * ja] - mx, a1 = tl[3 * ja + 1] - my, a2 = tl[3 * ja + 2] - mz;
+            const double b0 = tl[3 * jb] - mx, b1 = tl[3 * jb + 1] - my, b2 = tl[3 * jb + 2] - mz;
+            const double qa = __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
+            const double qb = __dadd_rn(__dadd_rn(__dmul_rn(b0, b0), __dmul_rn(b1, b1)), __dmul_rn(b2, b2));
+            if (qa < bd2) {                               // ascending j within a slice: first min kept
+                const double d = sqrt(qa);
+                if (d < bd) { bd = d; bd2 = qa; bj = t0 + ja; }
+            }
+            if (qb < bd2) {
+                const double d = sqrt(qb);
+                if (d < bd) { bd = d; bd2 = qb; bj = t0 + jb; }
+            }
+        }
+        for (; j < tn; j += PM_ICP_SLICES) {
+            const double d0 = tl[3 * j] - mx, d1 = tl[3 * j + 1] - my, d2 = tl[3 * j + 2] - mz;
             const double q2 = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
-            if (q2 < bd2) {                               // ascending j within a slice: first min kept
+            if (q2 < bd2) {
                 const double d = sqrt(q2);
                 if (d < bd) { bd = d; bd2 = q2; bj = t0 + j; }
             }
         }
+        __syncthreads();
     }
     best_d[s][p] = bd;
     best_j[s][p] = bj;
