@@ -1027,6 +1027,14 @@ __global__ void __launch_bounds__(PM_LAP_MAX_THREADS, 1) pm_lap_sap_kernel(PmLap
 // dynamic shared memory: v f64[ncp] | d f64[ncp] | pred u16[ncp] | r4c u16[ncp] | front u16[ncp] | scanned u8[ncp]
 #define PM_SS_THREADS 1024
 
+// warp arg-min over (value, tie) in lexicographic order with three REDUX instead of 15 shuffles
+__device__ __forceinline__ void pm_ss_argmin_warp(double &val, int &tie) {
+    const unsigned long long k = pm_ordkey(val);
+    const unsigned long long kb = pm_warp_min_u64(k);
+    tie = (int)__reduce_min_sync(0xffffffffu, k == kb ? (unsigned)tie : 0xffffffffu);
+    val = pm_ordval(kb);
+}
+
 __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmLapBatch B) {
     extern __shared__ __align__(16) unsigned char pm_ss_smem[];
     const PmLapView V = pm_lap_view(B, blockIdx.x);
@@ -1090,9 +1098,10 @@ __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmL
             // ---- add row i (distance dist) to the tree: relax its list edges, record its bound
             const double ui = __ldcg(V.u + i);
             if (t < PM_LS_K) {
-                const int j = __ldcg(V.lcol + (size_t)i * PM_LS_K + t);
+                const int j = __ldcg(V.lcol + (size_t)i * PM_LS_K + t);          // both list loads in flight together
+                const float cij = __ldcg(V.lcost + (size_t)i * PM_LS_K + t);
                 if (j >= 0 && !scanned[j]) {
-                    const double r = ((dist + (double)__ldcg(V.lcost + (size_t)i * PM_LS_K + t)) - ui) - v[j];
+                    const double r = ((dist + (double)cij) - ui) - v[j];
                     const double old = d[j];
                     if (r < old) {
                         if (!(old < INFINITY)) front[atomicAdd(&s_nfront, 1)] = (unsigned short)j;   // first time reached
@@ -1119,12 +1128,12 @@ __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmL
                         if (dj < best || (dj == best && tie < best_tie)) { best = dj; best_tie = tie; }
                     }
                 }
-                pm_argmin_warp(best, best_tie);
+                pm_ss_argmin_warp(best, best_tie);
                 if (lane == 0) { s_val[parity][warp] = best; s_tie[parity][warp] = best_tie; }
                 __syncthreads();
                 best = s_val[parity][lane];
                 best_tie = s_tie[parity][lane];
-                pm_argmin_warp(best, best_tie);
+                pm_ss_argmin_warp(best, best_tie);
                 parity ^= 1;
                 const double lam = s_lam;
                 const int lam_idx = s_lam_idx;
