@@ -35,6 +35,7 @@ TRIALS = 8000
 ICP_ITERS = 50
 FLOP_PER_PAIR = 1801.0        # 5 FLOP per bin pair x 360 + 1
 METRIC = "registrations/sec"
+CHI2_NCU_DRAM_BYTES = 186.0e6     # measured once with ncu at the headline size (10.6 MB read + 175.4 MB written)
 
 
 def parse():
@@ -312,11 +313,13 @@ def run_b200(args):
     sm = lib.pm_sm_count(local)
     for _ in range(2):
         lib.pm_probe_fp32_fma(sm * 8, 2000, D.ptr(sink), ctypes.byref(flops), D.stream_ptr())
-    e0.record()
-    lib.pm_probe_fp32_fma(sm * 8, 20000, D.ptr(sink), ctypes.byref(flops), D.stream_ptr())
-    e1.record()
-    torch.cuda.synchronize()
-    fp32_peak = flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    fp32_peak = 0.0
+    for _ in range(3):                       # best of 3: the denominator is a peak, not an average
+        e0.record()
+        lib.pm_probe_fp32_fma(sm * 8, 20000, D.ptr(sink), ctypes.byref(flops), D.stream_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        fp32_peak = max(fp32_peak, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -352,7 +355,10 @@ def run_b200(args):
                      "unit": "TFLOP/s", "frac": chi2_tflops / fp32_peak,
                      "peak_source": "FFMA probe kernel run in this process (MEASURED_PEAKS.json has no FP32 CUDA-core "
                                     "figure); nominal 2*128*148*1.965 GHz = 74.4",
-                     "flop_per_pair": FLOP_PER_PAIR, "launch_ms": chi2_ms, "traffic": None,
+                     "flop_per_pair": FLOP_PER_PAIR, "launch_ms": chi2_ms,
+                     "traffic": CHI2_NCU_DRAM_BYTES if (n1, n2) == (7200, 8000) else None,
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                                       "(profiles/r1_chi2_kernel.txt); algorithmic bytes: %.0f" % chi2_bytes,
                      "hbm": {"achieved": chi2_bytes / (chi2_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": chi2_bytes / (chi2_ms * 1e-3) / 1e9 / hbm_peak, "of": "measured"}},
         "stages_ms": stage_ms,

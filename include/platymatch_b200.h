@@ -58,6 +58,23 @@ int pm_probe_fp32_fma(int blocks, int iters, float *sink, double *flops_out, voi
  * divided by n-1), stats[12] n, stats[13:16] eigenvalues descending.  All float64 on device. */
 int pm_cloud_stats(const double *pts, int n, double *stats, void *stream);
 
+/* ---- label image -> detections --------------------------------------------
+ * The per-id loops of _dock_widget.py:497-521: for every non-zero id (ascending, np.unique order)
+ * centroid = mean z / y / x of its voxels, size = anisotropy * voxel count.  One streaming pass over
+ * the volume (HBM-bound); exact integer sums, so the means equal np.mean bit for bit.
+ *   labels      [nz][ny][nx] int32 (PM_LABEL_I32) or uint16 (PM_LABEL_U16), device; ids <= 0 = background
+ *   table_size  > largest id (pm_label_max_id finds it); ids >= table_size are ignored
+ *   ids [capacity] int32, centroids [capacity][3] float64 (z, y, x), sizes [capacity] float64,
+ *   n_out [1] int32 = number of non-empty ids (may exceed capacity: then only the first are written)
+ * workspace: pm_label_workspace_bytes(table_size). */
+#define PM_LABEL_I32 0
+#define PM_LABEL_U16 1
+int pm_label_max_id(const void *labels, int dtype, size_t n_voxels, uint32_t *max_id, void *stream);
+size_t pm_label_workspace_bytes(uint32_t table_size);
+int pm_label_centroids(const void *labels, int dtype, int nz, int ny, int nx, uint32_t table_size, double anisotropy,
+                       int capacity, int32_t *ids, double *centroids, double *sizes, int32_t *n_out, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
 /* ---- K1  mean pairwise distance -------------------------------------------------------------
  * get_mean_distance (utils.py:58-75): mean of ||p_i - p_j|| over unordered pairs.  Deterministic
  * (fixed-order two-level reduction).  out_mean: 1 float64 on device.

@@ -347,3 +347,29 @@ def estimate_transform_supervised(moving, fixed, moving_keypoints, fixed_keypoin
     a_sc = get_affine_transform(moving_keypoints, fixed_keypoints)
     a_icp, resid = perform_icp(apply_affine_transform(moving, a_sc), fixed, icp_iterations, return_residuals=True)
     return dict(transform_sc=a_sc, transform_icp=a_icp, transform=a_icp @ a_sc, icp_residuals=resid)
+
+
+# ---------------------------------------------------------------------------------------------
+# label image -> detections (reference platymatch/_dock_widget.py:497-521, inline
+# in EstimateTransform._click_run; restated line by line, the reference offers no callable for it)
+def detections_from_labels(label_image, anisotropy=1.0):
+    """ids = np.unique(data), 0 dropped (:497-500); per id: z, y, x = np.where(data == id),
+    centroid = (np.mean(z), np.mean(y), np.mean(x)) (:505-507), size = anisotropy * len(z) (:508).
+    Returns (detections 3 x N zyx, sizes N, ids N)."""
+    data = np.asarray(label_image)
+    ids = np.unique(data)
+    ids = ids[ids != 0]
+    temp, sizes = [], []
+    for id_ in ids:
+        z, y, x = np.where(data == id_)
+        temp.append([np.mean(z), np.mean(y), np.mean(x)])
+        sizes.append(float(anisotropy) * len(z))
+    det = np.asarray(temp, dtype=np.float64).reshape(-1, 3).transpose()
+    return det, np.asarray(sizes, dtype=np.float64), ids
+
+
+def ransac_error_from_sizes(moving_nucleus_size, fixed_nucleus_size):
+    """reference _dock_widget.py:613-618."""
+    if len(moving_nucleus_size) == 0 or len(fixed_nucleus_size) == 0:
+        return 16
+    return 0.5 * (np.average(moving_nucleus_size) ** (1 / 3) + np.average(fixed_nucleus_size) ** (1 / 3))

@@ -194,3 +194,34 @@ def compose(a16, b16):
     c = torch.empty(16, dtype=torch.float64, device=a16.device)
     check(load().pm_compose(ptr(a16), ptr(b16), ptr(c), stream_ptr()), "pm_compose")
     return c
+
+
+def label_centroids(labels, anisotropy=1.0, table_size=None):
+    """Label volume [nz, ny, nx] (CUDA int32 or uint16 tensor) -> (ids [n] i32, centroids [n,3] f64 zyx, sizes [n] f64),
+    ids ascending (np.unique order, 0 / negatives = background).  One streaming pass (pm_label_centroids)."""
+    torch = _torch()
+    assert labels.dim() == 3 and labels.is_cuda
+    labels = labels.contiguous()
+    if labels.dtype == torch.int32:
+        dtype = 0
+    elif labels.dtype == torch.uint16:
+        dtype = 1
+    else:
+        raise ValueError("label volume must be int32 or uint16, got %s" % labels.dtype)
+    nz, ny, nx = labels.shape
+    dev = labels.device
+    if table_size is None:
+        mx = torch.zeros(1, dtype=torch.int32, device=dev)
+        check(load().pm_label_max_id(ptr(labels), dtype, labels.numel(), ptr(mx), stream_ptr()), "pm_label_max_id")
+        table_size = int(mx.item()) + 1
+    cap = max(table_size - 1, 1)
+    ids = torch.empty(cap, dtype=torch.int32, device=dev)
+    cen = torch.empty((cap, 3), dtype=torch.float64, device=dev)
+    sizes = torch.empty(cap, dtype=torch.float64, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int32, device=dev)
+    nbytes = load().pm_label_workspace_bytes(table_size)
+    ws = torch.empty(nbytes // 8 + 1, dtype=torch.int64, device=dev)
+    check(load().pm_label_centroids(ptr(labels), dtype, nz, ny, nx, table_size, float(anisotropy), cap, ptr(ids), ptr(cen),
+                                    ptr(sizes), ptr(n_out), ptr(ws), nbytes, stream_ptr()), "pm_label_centroids")
+    n = min(int(n_out.item()), cap)
+    return ids[:n], cen[:n], sizes[:n]

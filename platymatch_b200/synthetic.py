@@ -69,3 +69,29 @@ def make_specimens(n_specimens=12, n_nuclei=8000, jitter=2.0, dropout=0.10, seed
         keep = r.permutation(atlas.shape[1])[:n_nuclei]
         out.append({"points": np.ascontiguousarray(pts[:, keep]), "A": a, "atlas_index": keep})
     return out
+
+
+def make_label_volume(shape=(64, 96, 128), n_nuclei=60, radius=(3.0, 6.0), seed=0, dtype=np.int32, sparse_ids=False,
+                      centers=None):
+    """Instance-segmentation volume: `n_nuclei` non-overlapping-ish balls with ids 1..n (or sparse, shuffled ids),
+    0 = background.  Later balls overwrite earlier ones, some ids may end up partially or fully covered.
+    centers: optional (n, 3) zyx ball centres (default: uniform in the volume)."""
+    rng = np.random.default_rng(seed)
+    nz, ny, nx = shape
+    if centers is not None:
+        n_nuclei = len(centers)
+    vol = np.zeros(shape, dtype=np.int64)
+    ids = np.arange(1, n_nuclei + 1)
+    if sparse_ids:
+        ids = np.sort(rng.choice(np.arange(1, 20 * n_nuclei), n_nuclei, replace=False))
+        ids = rng.permutation(ids)
+    zz, yy, xx = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij", sparse=True)
+    for k in range(n_nuclei):
+        c = rng.random(3) * np.array(shape) if centers is None else np.asarray(centers[k], dtype=np.float64)
+        r = rng.uniform(*radius)
+        z0, z1 = int(max(c[0] - r, 0)), int(min(c[0] + r + 1, nz))
+        y0, y1 = int(max(c[1] - r, 0)), int(min(c[1] + r + 1, ny))
+        x0, x1 = int(max(c[2] - r, 0)), int(min(c[2] + r + 1, nx))
+        sub = ((zz[z0:z1] - c[0]) ** 2 + (yy[:, y0:y1] - c[1]) ** 2 + (xx[:, :, x0:x1] - c[2]) ** 2) <= r * r
+        vol[z0:z1, y0:y1, x0:x1][sub] = ids[k]
+    return vol.astype(dtype)

@@ -368,6 +368,46 @@ def test_pipeline_supervised_vs_reference_goldens(torch):
         assert np.abs(res["transform"] - g["A_kp_icp"] @ g["A_kp"]).max() < 1e-4
 
 
+def test_supervised_8k_keypoints(O, torch):
+    """BASELINE config 3 (8k pair, 10 keypoint matches): LS affine on the keypoints + ICP, as the reference's
+    supervised branch (_dock_widget.py:707-717).  Checked against the oracle port on the same inputs (the
+    init and 3 ICP iterations: the CPU distance matrices of 50 would take minutes) and against the ground truth."""
+    import platymatch_b200 as pm
+    from platymatch_b200.synthetic import make_keypoints
+    p = _pair(8000)
+    mk, fk = make_keypoints(p, 10, seed=4)
+    res3 = pm.estimate_transform_supervised(p["moving"], p["fixed"], mk, fk, icp_iterations=3)
+    a_kp = O.get_affine_transform(mk, fk)
+    assert np.allclose(res3["transform_sc"], a_kp, rtol=1e-8, atol=1e-8)
+    a_icp = O.perform_icp(O.apply_affine_transform(p["moving"], a_kp), p["fixed"], 3)
+    assert np.abs(res3["transform"] - a_icp @ a_kp).max() < 1e-4
+    res = pm.estimate_transform_supervised(p["moving"], p["fixed"], mk, fk)           # 50 iterations
+    moved = O.apply_affine_transform(p["moving"], res["transform"])
+    err = np.linalg.norm(moved - p["fixed"][:, p["gt_fixed_index"]], axis=0)
+    assert np.median(err) < 4.0, np.median(err)
+    assert res["icp_residuals"][-1] <= res["icp_residuals"][0]
+
+
+def test_registration_12k(O, torch):
+    """Beyond the 8k config: 10800 x 12000, sparse auction + sparse augmenting paths at a size where the tail
+    kernel's ring still fits in shared memory; the true hypothesis wins and the transform maps nuclei onto
+    their partners; the LAP cost does not exceed the ground-truth matching's on the same matrix."""
+    import platymatch_b200 as pm
+    p = _pair(12000)
+    res = pm.estimate_transform_unsupervised(p["moving"], p["fixed"], ransac_trials=2000, keep_cost=True, seed=1)
+    best = res["best"]
+    n1 = p["moving"].shape[1]
+    cost = res["cost"][best][:, :12000].astype(np.float64)
+    fix_idx = res["assignments"][best][1]
+    assert len(np.unique(fix_idx)) == len(fix_idx) == n1
+    assert res["lap_cost"][best] <= cost[np.arange(n1), p["gt_fixed_index"]].sum() + 1e-9
+    assert res["lap_cost"][best] == pytest.approx(cost[np.arange(n1), fix_idx].sum(), rel=1e-12)
+    moved = O.apply_affine_transform(p["moving"], res["transform"])
+    err = np.linalg.norm(moved - p["fixed"][:, p["gt_fixed_index"]], axis=0)
+    assert np.median(err) < 4.0, np.median(err)
+    assert res["inliers"][best] > 3 * np.delete(res["inliers"], best).max()
+
+
 def test_pipeline_tall_problem(O, torch):
     """More moving than fixed nuclei: solved through the transpose like scipy, pairs ordered by moving index."""
     import platymatch_b200 as pm
