@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--bid-rounds", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stages", action="store_true", help="print a per-stage device-time breakdown to stderr")
+    ap.add_argument("--no-rows", action="store_true", help="skip the secondary measurements of the widened rows")
     ap.add_argument("--lean", action="store_true",
                     help="profiling aid: warm-up + timed resident steps only (no e2e, stage, roofline or CPU legs)")
     return ap.parse_args()
@@ -134,6 +135,53 @@ def run_reference(args):
                              "cost_matrix_gpairs_per_s": last["gpairs_per_s"]},
             "e2e": {"value": val, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- widened rows
+def bench_label_row(torch, D, hbm_peak, with_cpu):
+    """label volume -> detections (reference _dock_widget.py:497-521).  HBM-bound streaming
+    kernel: algorithmic bytes = one read of the volume; roofline against the measured copy bandwidth."""
+    from platymatch_b200.synthetic import make_label_volume
+    shape, n_nuclei = (384, 512, 512), 6000
+    rng = np.random.default_rng(1)
+    d = rng.normal(size=(n_nuclei, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    centers = np.array(shape) / 2.0 + d * (np.array(shape) * 0.42) + rng.normal(0, 4.0, size=(n_nuclei, 3))
+    vol = make_label_volume(shape, radius=(3.0, 5.0), seed=2, centers=centers, dtype=np.int32)
+    dev = torch.from_numpy(vol).cuda()
+    nbytes = vol.size * 4
+    for _ in range(3):
+        ids, cen, sizes = D.label_centroids(dev, 1.0, table_size=n_nuclei + 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    flush = torch.empty(160 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+    ms = 0.0
+    for _ in range(reps):
+        flush.fill_(1)
+        e0.record()
+        D.label_centroids(dev, 1.0, table_size=n_nuclei + 1, sync=False)          # memset + accumulate + compact
+        e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1) / reps
+    out = {"workload": "label volume %dx%dx%d int32, %d nuclei (%.0f %% foreground)" %
+                       (shape + (int(ids.numel()), 100.0 * float((vol > 0).mean()))),
+           "ms": ms, "voxels_per_s": vol.size / (ms * 1e-3),
+           "roofline": {"kernel": "pm_label_accumulate_kernel", "bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9,
+                        "peak": hbm_peak, "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak, "of": "measured",
+                        "algorithmic_bytes": nbytes, "l2": "160 MB flush between repetitions"}}
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as O
+        k = 4                                          # the reference makes one np.where pass over the volume per id
+        sub = vol.copy()
+        keep = np.isin(sub, np.unique(sub[sub > 0])[:k])
+        sub[~keep] = 0
+        t0 = time.perf_counter()
+        O.detections_from_labels(sub, 1.0)
+        t = (time.perf_counter() - t0) / k * int(ids.numel())
+        out["cpu_baseline"] = {"value": vol.size / t, "unit": "voxels/s", "cores": 1, "kind": "port",
+                               "sample": "oracle restatement of the per-id np.where loop: %d of %d ids timed, scaled" % (k, int(ids.numel()))}
+    return out
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
@@ -369,6 +417,8 @@ def run_b200(args):
                       "refresh_cycles": [s[9] for s in lap_stats], "auction_cycles": [s[10] for s in lap_stats],
                       "bulk_bids": [s[11] for s in lap_stats], "sap_dense_relax": [s[12] for s in lap_stats]},
     }
+    if not args.no_rows:
+        line["rows"] = {"label_centroids": bench_label_row(torch, D, hbm_peak, not args.no_cpu_baseline)}
     if not args.no_cpu_baseline:
         cb = cpu_sample(pairs[0], args.trials, ICP_ITERS)
         line["cpu_baseline"] = {"value": 1.0 / cb["seconds_per_registration"], "unit": "registrations/s",

@@ -5,17 +5,13 @@
 // mean x); size = anisotropy * len(z) — one full pass over the volume PER ID (O(ids x voxels)).
 //
 // Here: ONE streaming pass over the volume (HBM-bound: 4 B per voxel read once).  Every thread
-// loads four consecutive voxels; lanes of a warp that hold the same non-zero id form a group
-// (cooperative-groups labeled_partition = match.any), the group's voxel count and coordinate sums
-// are reduced in registers and its leader issues four 64-bit atomic adds on the id's accumulator
+// loads 4 x four consecutive voxels; lanes of a warp that hold the same non-zero id form a group
+// (match.any), the group's voxel count and coordinate sums are reduced with REDUX and its leader
+// issues four 64-bit atomic adds on the id's accumulator
 // {count, sum z, sum y, sum x}.  The sums are exact integers, so mean = sum / count rounds once and
 // equals np.mean of the integer coordinates bit for bit (sums stay far below 2^53).
 // A second small kernel compacts the non-empty ids in ascending order (np.unique order).
-#include <cooperative_groups.h>
-#include <cooperative_groups/reduce.h>
 #include "pm_common.cuh"
-
-namespace cg = cooperative_groups;
 
 template <typename T>
 __global__ void __launch_bounds__(256) pm_label_max_kernel(const T *__restrict__ labels, size_t n_vox,
@@ -32,47 +28,101 @@ __global__ void __launch_bounds__(256) pm_label_max_kernel(const T *__restrict__
 }
 
 template <typename T>
+__device__ __forceinline__ void pm_label_load4(const T *__restrict__ labels, size_t base, size_t n_vox, bool aligned,
+                                               int ids[4]) {
+    if (base + 3 < n_vox && aligned) {          // one 16- / 8-byte load
+        if (sizeof(T) == 4) {
+            const int4 q = __ldcs(reinterpret_cast<const int4 *>(labels + base));     // streamed once: evict first
+            ids[0] = q.x; ids[1] = q.y; ids[2] = q.z; ids[3] = q.w;
+        } else {
+            const ushort4 q = __ldcs(reinterpret_cast<const ushort4 *>(labels + base));
+            ids[0] = q.x; ids[1] = q.y; ids[2] = q.z; ids[3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ids[e] = (base + e < n_vox) ? (int)labels[base + e] : 0;
+    }
+}
+
+#define PM_LABEL_UNROLL 4      // independent 16-byte loads in flight per thread
+
+struct PmVox { unsigned z, y, x; };
+
+// advance a voxel coordinate by a fixed linear step given as (dz, dy, dx), dy < ny, dx < nx
+__device__ __forceinline__ void pm_vox_advance(PmVox &v, const PmVox &d, unsigned ny, unsigned nx) {
+    v.x += d.x;
+    unsigned cy = 0;
+    if (v.x >= nx) { v.x -= nx; cy = 1; }
+    v.y += d.y + cy;
+    unsigned cz = 0;
+    if (v.y >= ny) { v.y -= ny; cz = 1; }
+    v.z += d.z + cz;
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256) pm_label_accumulate_kernel(const T *__restrict__ labels, int nz, int ny, int nx,
                                                                   unsigned table_size,
                                                                   unsigned long long *__restrict__ acc) {
     const size_t n_vox = (size_t)nz * ny * nx;
     const size_t plane = (size_t)ny * nx;
-    const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
-    for (size_t base = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; base < n_vox; base += stride) {
-        long long ids[4];
-        if (base + 3 < n_vox && (reinterpret_cast<size_t>(labels) & 15) == 0) {   // one 16- / 8-byte load
-            if (sizeof(T) == 4) {
-                const int4 q = *reinterpret_cast<const int4 *>(labels + base);
-                ids[0] = q.x; ids[1] = q.y; ids[2] = q.z; ids[3] = q.w;
-            } else {
-                const ushort4 q = *reinterpret_cast<const ushort4 *>(labels + base);
-                ids[0] = q.x; ids[1] = q.y; ids[2] = q.z; ids[3] = q.w;
+    const size_t sweep = (size_t)gridDim.x * blockDim.x * 4;          // voxels covered by one load of the whole grid
+    const bool aligned = (reinterpret_cast<size_t>(labels) & 15) == 0;
+    const int lane = threadIdx.x & 31;
+    // voxel coordinates of this thread's first voxel and of one sweep: 64-bit divisions once, carries afterwards
+    const size_t first = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    PmVox pos, step;
+    pos.z = (unsigned)(first / plane);
+    pos.y = (unsigned)((first - (size_t)pos.z * plane) / nx);
+    pos.x = (unsigned)(first - (size_t)pos.z * plane - (size_t)pos.y * nx);
+    step.z = (unsigned)(sweep / plane);
+    step.y = (unsigned)((sweep - (size_t)step.z * plane) / nx);
+    step.x = (unsigned)(sweep - (size_t)step.z * plane - (size_t)step.y * nx);
+    // the trip count is uniform across a warp (bounds are checked per load), so the warp stays converged for
+    // the match / redux collectives below
+    const size_t warp_base = ((size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * 4;
+    for (size_t wb = warp_base; wb < n_vox; wb += sweep * PM_LABEL_UNROLL) {
+        int ids[PM_LABEL_UNROLL][4];
+        bool any_fg = false;
+#pragma unroll
+        for (int u = 0; u < PM_LABEL_UNROLL; ++u) {
+            const size_t base = wb + (size_t)u * sweep + (size_t)lane * 4;
+            ids[u][0] = ids[u][1] = ids[u][2] = ids[u][3] = 0;
+            if (base < n_vox) pm_label_load4(labels, base, n_vox, aligned, ids[u]);
+            any_fg |= (ids[u][0] | ids[u][1] | ids[u][2] | ids[u][3]) != 0;
+        }
+        if (__any_sync(0xffffffffu, any_fg)) {
+#pragma unroll
+            for (int u = 0; u < PM_LABEL_UNROLL; ++u) {
+                const bool fg = (ids[u][0] | ids[u][1] | ids[u][2] | ids[u][3]) != 0;
+                if (__any_sync(0xffffffffu, fg)) {
+                    PmVox p = pos;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int id = ids[u][e];
+                        const bool valid = id > 0 && (unsigned)id < table_size;
+                        const unsigned voters = __ballot_sync(0xffffffffu, valid);
+                        if (voters != 0u && valid) {
+                            // lanes holding the same id: one group, its sums by REDUX, one leader
+                            const unsigned peers = __match_any_sync(voters, (unsigned)id);
+                            const unsigned sz = __reduce_add_sync(peers, p.z);
+                            const unsigned sy = __reduce_add_sync(peers, p.y);
+                            const unsigned sx = __reduce_add_sync(peers, p.x);
+                            if (lane == __ffs(peers) - 1) {
+                                unsigned long long *a = acc + (size_t)id * 4;
+                                atomicAdd(a + 0, (unsigned long long)__popc(peers));
+                                atomicAdd(a + 1, (unsigned long long)sz);
+                                atomicAdd(a + 2, (unsigned long long)sy);
+                                atomicAdd(a + 3, (unsigned long long)sx);
+                            }
+                        }
+                        if (++p.x >= (unsigned)nx) { p.x = 0; if (++p.y >= (unsigned)ny) { p.y = 0; ++p.z; } }
+                    }
+                }
+                pm_vox_advance(pos, step, (unsigned)ny, (unsigned)nx);
             }
         } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) ids[e] = (base + e < n_vox) ? (long long)labels[base + e] : 0;
-        }
-        if ((ids[0] | ids[1] | ids[2] | ids[3]) == 0) continue;        // background (most of the volume)
-        const unsigned z0 = (unsigned)(base / plane);
-        const size_t rem = base - (size_t)z0 * plane;
-        const unsigned y0 = (unsigned)(rem / nx), x0 = (unsigned)(rem - (size_t)y0 * nx);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (ids[e] <= 0 || (unsigned long long)ids[e] >= table_size) continue;
-            unsigned x = x0 + e, y = y0, z = z0;
-            while (x >= (unsigned)nx) { x -= nx; if (++y >= (unsigned)ny) { y = 0; ++z; } }
-            const cg::coalesced_group active = cg::coalesced_threads();
-            const cg::coalesced_group grp = cg::labeled_partition(active, (unsigned)ids[e]);
-            const unsigned sz = cg::reduce(grp, z, cg::plus<unsigned>());
-            const unsigned sy = cg::reduce(grp, y, cg::plus<unsigned>());
-            const unsigned sx = cg::reduce(grp, x, cg::plus<unsigned>());
-            if (grp.thread_rank() == 0) {
-                unsigned long long *a = acc + (size_t)ids[e] * 4;
-                atomicAdd(a + 0, (unsigned long long)grp.size());
-                atomicAdd(a + 1, (unsigned long long)sz);
-                atomicAdd(a + 2, (unsigned long long)sy);
-                atomicAdd(a + 3, (unsigned long long)sx);
-            }
+            for (int u = 0; u < PM_LABEL_UNROLL; ++u) pm_vox_advance(pos, step, (unsigned)ny, (unsigned)nx);
         }
     }
 }

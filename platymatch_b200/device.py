@@ -196,7 +196,7 @@ def compose(a16, b16):
     return c
 
 
-def label_centroids(labels, anisotropy=1.0, table_size=None):
+def label_centroids(labels, anisotropy=1.0, table_size=None, sync=True):
     """Label volume [nz, ny, nx] (CUDA int32 or uint16 tensor) -> (ids [n] i32, centroids [n,3] f64 zyx, sizes [n] f64),
     ids ascending (np.unique order, 0 / negatives = background).  One streaming pass (pm_label_centroids)."""
     torch = _torch()
@@ -223,5 +223,7 @@ def label_centroids(labels, anisotropy=1.0, table_size=None):
     ws = torch.empty(nbytes // 8 + 1, dtype=torch.int64, device=dev)
     check(load().pm_label_centroids(ptr(labels), dtype, nz, ny, nx, table_size, float(anisotropy), cap, ptr(ids), ptr(cen),
                                     ptr(sizes), ptr(n_out), ptr(ws), nbytes, stream_ptr()), "pm_label_centroids")
+    if not sync:                      # everything is enqueued; the caller reads n_out later
+        return ids, cen, sizes, n_out
     n = min(int(n_out.item()), cap)
     return ids[:n], cen[:n], sizes[:n]
