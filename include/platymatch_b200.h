@@ -75,6 +75,12 @@ int pm_label_centroids(const void *labels, int dtype, int nz, int ny, int nx, ui
                        int capacity, int32_t *ids, double *centroids, double *sizes, int32_t *n_out, void *workspace,
                        size_t workspace_bytes, void *stream);
 
+/* ---- Euclidean distance matrix ----------------------------------------------
+ * scipy.spatial.distance.cdist as called by EvaluateMetrics._calculate_metrics (_dock_widget.py:1032,
+ * 1038,1050): out[i * ldo + j] = ||a_i - b_j|| (float64 arithmetic, stored as the float32 costs the
+ * assignment kernel consumes).  a [n1][3], b [n2][3] float64. */
+int pm_cdist(const double *a, int n1, const double *b, int n2, float *out, int ldo, void *stream);
+
 /* ---- K1  mean pairwise distance -------------------------------------------------------------
  * get_mean_distance (utils.py:58-75): mean of ||p_i - p_j|| over unordered pairs.  Deterministic
  * (fixed-order two-level reduction).  out_mean: 1 float64 on device.

@@ -373,3 +373,38 @@ def ransac_error_from_sizes(moving_nucleus_size, fixed_nucleus_size):
     if len(moving_nucleus_size) == 0 or len(fixed_nucleus_size) == 0:
         return 16
     return 0.5 * (np.average(moving_nucleus_size) ** (1 / 3) + np.average(fixed_nucleus_size) ** (1 / 3))
+
+
+# ---------------------------------------------------------------------------------------------
+# EvaluateMetrics._calculate_metrics (reference platymatch/_dock_widget.py:1030-1080),
+# restated with scipy's cdist + linear_sum_assignment exactly as the reference calls them.
+def calculate_metrics(moving_keypoints, moving_keypoint_ids, moving_detections, moving_ids,
+                      fixed_keypoints, fixed_keypoint_ids, fixed_detections, fixed_ids,
+                      transform_matrix_1, transform_matrix_2=None):
+    from scipy.optimize import linear_sum_assignment as lsa
+    from scipy.spatial.distance import cdist
+    t2 = np.eye(4) if transform_matrix_2 is None else transform_matrix_2
+    r, c = lsa(cdist(moving_keypoints.transpose(), moving_detections.transpose()))          # :1032-1033
+    moving_dictionary = {}
+    for index in r:
+        moving_dictionary[moving_keypoint_ids[index]] = moving_ids[c[index]]
+    r, c = lsa(cdist(fixed_keypoints.transpose(), fixed_detections.transpose()))            # :1038-1039
+    fixed_dictionary = {}
+    for index in r:
+        fixed_dictionary[fixed_keypoint_ids[index]] = fixed_ids[c[index]]
+    moved = apply_affine_transform(apply_affine_transform(moving_detections, transform_matrix_1), t2)   # :1044-1046
+    row_indices, col_indices = lsa(cdist(moved.transpose(), fixed_detections.transpose()))  # :1050-1051
+    row_ids, col_ids = moving_ids[row_indices], fixed_ids[col_indices]
+    hits = 0
+    for key in moving_dictionary.keys():
+        if key in fixed_dictionary.keys():
+            if col_ids[np.where(row_ids == moving_dictionary[key])] == fixed_dictionary[key]:
+                hits += 1
+    accuracy = hits / len(fixed_dictionary.keys())                                          # :1067
+    combined = np.matmul(t2, transform_matrix_1)                                            # :1028
+    moved_kp = apply_affine_transform(moving_keypoints, combined)
+    distance = 0
+    for i in range(moved_kp.shape[1]):
+        distance += np.linalg.norm([fixed_keypoints.transpose()[np.where(fixed_keypoint_ids == moving_keypoint_ids[i]), :]
+                                    - moved_kp.transpose()[i, :]])
+    return accuracy, distance / len(moving_dictionary.keys())                                # :1079

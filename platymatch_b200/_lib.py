@@ -27,6 +27,7 @@ SIGNATURES = {
     "pm_label_max_id": (_i, [_vp, _i, _sz, _vp, _vp]),
     "pm_label_workspace_bytes": (_sz, [ctypes.c_uint32]),
     "pm_label_centroids": (_i, [_vp, _i, _i, _i, _i, ctypes.c_uint32, _d, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pm_cdist": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp]),
     "pm_cloud_stats": (_i, [_vp, _i, _vp, _vp]),
     "pm_mean_distance_workspace_bytes": (_sz, [_i]),
     "pm_mean_distance": (_i, [_vp, _i, _vp, _vp, _sz, _vp]),

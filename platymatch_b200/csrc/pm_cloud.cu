@@ -279,3 +279,46 @@ extern "C" int pm_compose(const double *A, const double *B, double *C, void *str
     PM_LAUNCH_CHECK();
     return PM_OK;
 }
+
+// ---- Euclidean distance matrix (scipy.spatial.distance.cdist as used by EvaluateMetrics._calculate_metrics,
+// reference _dock_widget.py:1032,1038,1050): out[i][j] = ||a_i - b_j||, float64 arithmetic in numpy's
+// association order, rounded once to the float32 cost matrix the LAP kernel consumes.  One 16 x 16 thread
+// tile computes 64 x 64 outputs; both point blocks sit in shared memory.  HBM-bound (4 B written per pair).
+__global__ void __launch_bounds__(256) pm_cdist_kernel(const double *__restrict__ a, int n1, const double *__restrict__ b,
+                                                       int n2, float *__restrict__ out, int ldo) {
+    __shared__ double sa[64][3], sb[64][3];
+    const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+    for (int q = threadIdx.x; q < 192; q += 256) {
+        const int r = q / 3, c = q % 3;
+        sa[r][c] = (i0 + r < n1) ? a[(size_t)(i0 + r) * 3 + c] : 0.0;
+        sb[r][c] = (j0 + r < n2) ? b[(size_t)(j0 + r) * 3 + c] : 0.0;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + ty * 4 + r;
+        if (i >= n1) continue;
+        const double ax = sa[ty * 4 + r][0], ay = sa[ty * 4 + r][1], az = sa[ty * 4 + r][2];
+        float v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int jj = tx * 4 + c;
+            const double d0 = ax - sb[jj][0], d1 = ay - sb[jj][1], d2 = az - sb[jj][2];
+            v[c] = (float)sqrt(__dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2)));
+        }
+        float *row = out + (size_t)i * ldo + j0 + tx * 4;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (j0 + tx * 4 + c < n2) row[c] = v[c];
+    }
+}
+
+extern "C" int pm_cdist(const double *a, int n1, const double *b, int n2, float *out, int ldo, void *stream) {
+    PM_REQUIRE(a && b && out, "null pointer");
+    PM_REQUIRE(n1 >= 1 && n2 >= 1 && ldo >= n2, "need n1, n2 >= 1 and ldo >= n2");
+    dim3 grid((n2 + 63) / 64, (n1 + 63) / 64);
+    pm_cdist_kernel<<<grid, 256, 0, pm_stream(stream)>>>(a, n1, b, n2, out, ldo);
+    PM_LAUNCH_CHECK();
+    return PM_OK;
+}

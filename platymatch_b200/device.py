@@ -227,3 +227,13 @@ def label_centroids(labels, anisotropy=1.0, table_size=None, sync=True):
         return ids, cen, sizes, n_out
     n = min(int(n_out.item()), cap)
     return ids[:n], cen[:n], sizes[:n]
+
+
+def cdist(a, b):
+    """[n1,3], [n2,3] f64 -> [n1, ld] f32 Euclidean distances (ld = n2 rounded up to 4), as the LAP kernel wants them."""
+    torch = _torch()
+    n1, n2 = a.shape[0], b.shape[0]
+    ld = (n2 + 3) // 4 * 4
+    out = torch.zeros((n1, ld), dtype=torch.float32, device=a.device)
+    check(load().pm_cdist(ptr(a), n1, ptr(b), n2, ptr(out), ld, stream_ptr()), "pm_cdist")
+    return out

@@ -63,10 +63,15 @@ def test_no_cpu_fallback_without_device():
 
 
 def test_product_never_imports_oracle():
+    """The shipped package never imports, links or executes the CPU oracle, nor scipy / sklearn (comments that
+    cite the reference's third-party calls are fine)."""
+    import re
+    bad = re.compile(r"^\s*(import|from)\s+(oracle|scipy|sklearn)\b", re.M)
     for dirpath, _, files in os.walk(os.path.join(ROOT, "platymatch_b200")):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
-                assert "import oracle" not in src and "pm_oracle" not in src and "scipy" not in src.replace(
-                    "scipy.optimize.linear_sum_assignment", "").replace("scipy does", "").replace("as scipy", "").replace(
-                    "like scipy", "").replace("scipy solves", ""), os.path.join(dirpath, f)
+                assert "pm_oracle" not in src and "libpm_oracle" not in src, os.path.join(dirpath, f)
+                if f.endswith(".py"):
+                    assert not bad.search(src), os.path.join(dirpath, f)
+
