@@ -170,24 +170,50 @@ def register_pair_sharded(moving, fixed, *, ransac_samples=4, ransac_trials=8000
                 lap_cost=lap_cost, icp_residuals=resid.cpu().numpy())
 
 
-def register_all_pairs(specimens, *, group=None, **kw):
+def register_all_pairs(specimens, *, group=None, in_flight=3, **kw):
     """Batched all-pairs registration (config 5): descriptors of each specimen are computed once per rank
-    that needs them, pairs are sharded round-robin, the 4x4 results are gathered on every rank.
-    specimens: list of 3xN arrays.  Returns (pairs, transforms[n_pairs,4,4])."""
+    that needs them, pairs are sharded round-robin over the ranks, the 4x4 results are gathered on every rank.
+    On each rank `in_flight` independent registrations overlap on separate CUDA streams (one host thread each):
+    the assignment stage is latency-bound on a few SMs and hides behind the cost-matrix / ICP kernels of the
+    other pairs.  specimens: list of 3xN arrays.  Returns (pairs, transforms[n_pairs,4,4])."""
+    import threading
+    import torch
     from . import pipeline as P
     rank, world = world_info(group)
     pairs = all_pairs(len(specimens))
     mine = [(k, p) for k, p in enumerate(pairs) if k % world == rank]
     desc = {}
+    for _, (i, j) in mine:       # variants 1-2 double as the 'moving' sets
+        for s in (i, j):
+            if s not in desc:
+                desc[s] = P.describe_cloud(specimens[s], 4)
+    for d in desc.values():      # operands are built lazily: do it here, before the streams fork
+        for v in (1, 2, 3, 4):
+            d.operand(v)
+    torch.cuda.synchronize()
+    local, errors = {}, []
+    nfl = max(1, min(int(in_flight), len(mine)))
+    dev = torch.cuda.current_device()
 
-    def describe(s):
-        if s not in desc:
-            desc[s] = P.describe_cloud(specimens[s], 4)     # variants 1-2 double as the 'moving' sets
-        return desc[s]
+    def worker(w):
+        try:
+            torch.cuda.set_device(dev)
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for k, (i, j) in mine[w::nfl]:      # moving = specimen i, fixed = specimen j (tall problems are transposed inside)
+                    res = P.register_described(desc[i], desc[j], seed=k, **kw)
+                    local[k] = res["transform"].cpu().numpy().reshape(4, 4)
+        except Exception as e:     # surfaced below: a worker must not die silently
+            errors.append(e)
 
-    local = {}
-    for k, (i, j) in mine:       # moving = specimen i, fixed = specimen j (tall problems are transposed inside)
-        res = P.register_described(describe(i), describe(j), seed=k, **kw)
-        local[k] = res["transform"].cpu().numpy().reshape(4, 4)
+    if nfl == 1:
+        worker(0)
+    else:
+        ts = [threading.Thread(target=worker, args=(w,)) for w in range(nfl)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+    if errors:
+        raise errors[0]
     out = gather_results(local, len(pairs), None, group)
     return pairs, out.numpy().reshape(-1, 4, 4)
