@@ -336,7 +336,7 @@ def run_b200(args):
                     m, f = dev_pairs[s_ % n_slots]
                     dmk = P.describe_cloud(m, 1, transposed=True)
                     dfk = P.describe_cloud(f, 4, transposed=True)
-                    P.register_described(dmk, dfk, seed=s_, cost_out=bufs[k], **kw)
+                    P.register_described(dmk, dfk, seed=s_, cost_out=bufs[k], overlap_hypotheses=False, **kw)
 
         def run_all(steps):
             ts = [threading.Thread(target=worker, args=(k, steps)) for k in range(nfl)]

@@ -200,7 +200,7 @@ def register_all_pairs(specimens, *, group=None, in_flight=3, **kw):
             torch.cuda.set_device(dev)
             with torch.cuda.stream(torch.cuda.Stream()):
                 for k, (i, j) in mine[w::nfl]:      # moving = specimen i, fixed = specimen j (tall problems are transposed inside)
-                    res = P.register_described(desc[i], desc[j], seed=k, **kw)
+                    res = P.register_described(desc[i], desc[j], seed=k, overlap_hypotheses=(nfl == 1), **kw)
                     local[k] = res["transform"].cpu().numpy().reshape(4, 4)
         except Exception as e:     # surfaced below: a worker must not die silently
             errors.append(e)

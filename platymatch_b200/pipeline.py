@@ -8,6 +8,7 @@ results stays on the GPU; stage boundaries are stream-ordered kernel launches th
 import numpy as np
 
 from . import device as D
+from ._lib import LAP_STATS as _LAP_STATS
 
 __all__ = ["HYPOTHESES_REFERENCE", "HYPOTHESES_DISTINCT", "estimate_transform_unsupervised",
            "estimate_transform_supervised", "Descriptors", "describe_cloud", "register_described"]
@@ -57,11 +58,30 @@ def _draw_or_take(sample_indices, q):
     return s if torch.is_tensor(s) else torch.from_numpy(np.ascontiguousarray(s, dtype=np.int32)).cuda()
 
 
+_HYP_STREAMS = {}
+
+
+def _hypothesis_streams(device, n):
+    """High-priority side streams for the per-hypothesis assignment chains, cached per (device, caller stream):
+    concurrent callers (one host thread and stream each) must not share them."""
+    torch = D._torch()
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream().cuda_stream)
+    pool = _HYP_STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device, priority=-1))
+    return pool[:n]
+
+
 def register_described(dm, df, ransac_samples=4, ransac_trials=8000, ransac_error=16, icp_iterations=50,
                        hypotheses=None, seed=0, sample_indices=None, max_bid_rounds=2048, cost_out=None,
-                       keep_cost=False, stage_hook=None):
+                       keep_cost=False, stage_hook=None, overlap_hypotheses=True):
     """Cost matrices -> LAP -> RANSAC -> argmax -> ICP for two described clouds (device resident).
 
+    The H hypothesis chains {cost matrix -> assignment -> RANSAC} are independent (reference
+    _dock_widget.py:547-675 runs them one after the other).  With `overlap_hypotheses` each chain is enqueued
+    on its own CUDA stream: the assignment of one hypothesis is latency-bound on a few SMs and runs underneath
+    the compute-bound cost-matrix kernels of the next ones.  Results are identical either way.
     Returns a dict of CUDA tensors / python scalars; only `best` (one int) is read back in between
     (the reference's np.argmax over the inlier counts, _dock_widget.py:683-703).
     """
@@ -72,20 +92,29 @@ def register_described(dm, df, ransac_samples=4, ransac_trials=8000, ransac_erro
     nr, nc = (n2, n1) if swap else (n1, n2)
     ldc = (nc + 3) // 4 * 4
     H = len(hyps)
-    cost = cost_out if cost_out is not None else torch.empty((H, nr, ldc), dtype=torch.float32, device=dm.pts.device)
-    for q, (a, b) in enumerate(hyps):
+    dev = dm.pts.device
+    cost = cost_out if cost_out is not None else torch.empty((H, nr, ldc), dtype=torch.float32, device=dev)
+    ransac_a = torch.empty((H, 16), dtype=torch.float64, device=dev)
+    inliers = torch.empty(H, dtype=torch.int32, device=dev)
+    col4row = torch.empty((H, nr), dtype=torch.int32, device=dev)
+    lap_total = torch.empty(H, dtype=torch.float64, device=dev)
+    lap_stats = torch.empty((H, _LAP_STATS), dtype=torch.int64, device=dev)
+    rows_arange = torch.arange(nr, dtype=torch.int32, device=dev)
+    pairs = [None] * H
+    ops_m = {a: dm.operand(a) for a, _ in hyps}     # built on the caller's stream, before the chains fork
+    ops_f = {b: df.operand(b) for _, b in hyps}
+
+    def cost_matrix(q):
+        a, b = hyps[q]
         if swap:
-            D.chi2_cost(df.operand(b), dm.operand(a), out=cost[q])
+            D.chi2_cost(ops_f[b], ops_m[a], out=cost[q])
         else:
-            D.chi2_cost(dm.operand(a), df.operand(b), out=cost[q])
-    if stage_hook: stage_hook("chi2_cost")
-    col4row, lap_total, lap_stats = D.lap_solve(cost, nr, nc, max_bid_rounds)
-    if stage_hook: stage_hook("lap")
-    ransac_a = torch.empty((H, 16), dtype=torch.float64, device=dm.pts.device)
-    inliers = torch.empty(H, dtype=torch.int32, device=dm.pts.device)
-    pairs = []
-    rows_arange = torch.arange(nr, dtype=torch.int32, device=dm.pts.device)
-    for q in range(H):
+            D.chi2_cost(ops_m[a], ops_f[b], out=cost[q])
+
+    def assign_and_ransac(q, c4r, tot, st):
+        col4row[q].copy_(c4r)
+        lap_total[q:q + 1].copy_(tot)
+        lap_stats[q].copy_(st)
         if swap:                        # rows are fixed nuclei; reference order = ascending moving index
             mov_idx, order = torch.sort(col4row[q])
             fix_idx = rows_arange[order]
@@ -98,8 +127,33 @@ def register_described(dm, df, ransac_samples=4, ransac_trials=8000, ransac_erro
                                        _draw_or_take(sample_indices, q), seed=(int(seed) << 8) + q)
         ransac_a[q] = a
         inliers[q:q + 1] = inl
-        pairs.append((mov_idx, fix_idx))
-    if stage_hook: stage_hook("ransac")
+        pairs[q] = (mov_idx, fix_idx)
+
+    if overlap_hypotheses and stage_hook is None and H > 1:
+        # cost matrices stay on the caller's stream (compute-bound, every SM); each assignment + RANSAC chain
+        # goes to a high-priority side stream as soon as its matrix is done, so that its few, long-running CTAs
+        # are placed ahead of the queued cost-matrix CTAs of the next hypotheses
+        main = torch.cuda.current_stream()
+        sides = _hypothesis_streams(dev, H)
+        for q, side in enumerate(sides):
+            cost_matrix(q)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                c4r, tot, st = D.lap_solve(cost[q:q + 1], nr, nc, max_bid_rounds)
+                assign_and_ransac(q, c4r[0], tot, st[0])
+        for side in sides:
+            main.wait_stream(side)
+    else:
+        for q in range(H):
+            cost_matrix(q)
+        if stage_hook: stage_hook("chi2_cost")
+        c4r, tot, st = D.lap_solve(cost, nr, nc, max_bid_rounds)
+        if stage_hook: stage_hook("lap")
+        for q in range(H):
+            assign_and_ransac(q, c4r[q], tot[q:q + 1], st[q])
+        if stage_hook: stage_hook("ransac")
     best = int(torch.argmax(inliers).item())     # first maximum, as np.argmax (_dock_widget.py:683)
     a_sc = ransac_a[best].contiguous()
     moved = D.apply_affine(dm.pts, a_sc)                                   # :714
