@@ -1025,7 +1025,7 @@ __global__ void __launch_bounds__(PM_LAP_MAX_THREADS, 1) pm_lap_sap_kernel(PmLap
 // (exactly the dense algorithm's step) and its bound removed.  Same result as the dense search.
 //
 // dynamic shared memory: v f64[ncp] | d f64[ncp] | pred u16[ncp] | r4c u16[ncp] | front u16[ncp] | scanned u8[ncp]
-#define PM_SS_THREADS 1024
+#define PM_SS_THREADS 1024     // the reached frontier grows to most of the columns within ~60 steps: the scan wants every thread
 
 // warp arg-min over (value, tie) in lexicographic order with three REDUX instead of 15 shuffles
 __device__ __forceinline__ void pm_ss_argmin_warp(double &val, int &tie) {
@@ -1074,7 +1074,7 @@ __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmL
         __syncthreads();
         if (t == 0) {
             int acc = s_nfree;
-            for (int w = 0; w < 32; ++w) { const int c = s_scan[w]; s_scan[w] = acc; acc += c; }
+            for (int w = 0; w < PM_SS_THREADS / 32; ++w) { const int c = s_scan[w]; s_scan[w] = acc; acc += c; }
             s_scan[32] = acc;
         }
         __syncthreads();
@@ -1131,8 +1131,8 @@ __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmL
                 pm_ss_argmin_warp(best, best_tie);
                 if (lane == 0) { s_val[parity][warp] = best; s_tie[parity][warp] = best_tie; }
                 __syncthreads();
-                best = s_val[parity][lane];
-                best_tie = s_tie[parity][lane];
+                best = (lane < PM_SS_THREADS / 32) ? s_val[parity][lane] : INFINITY;
+                best_tie = (lane < PM_SS_THREADS / 32) ? s_tie[parity][lane] : INT_MAX;
                 pm_ss_argmin_warp(best, best_tie);
                 parity ^= 1;
                 const double lam = s_lam;
