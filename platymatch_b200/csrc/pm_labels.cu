@@ -95,27 +95,61 @@ __global__ void __launch_bounds__(256) pm_label_accumulate_kernel(const T *__res
             for (int u = 0; u < PM_LABEL_UNROLL; ++u) {
                 const bool fg = (ids[u][0] | ids[u][1] | ids[u][2] | ids[u][3]) != 0;
                 if (__any_sync(0xffffffffu, fg)) {
-                    PmVox p = pos;
+                    // common case: the (up to four) foreground voxels of a thread belong to ONE nucleus and sit in
+                    // one image row -> the thread contributes one pre-summed item, the warp needs one round
+                    int id1 = 0, k = 0;
+                    unsigned sxl = 0;
+                    bool simple = pos.x + 3 < (unsigned)nx;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int id = ids[u][e];
-                        const bool valid = id > 0 && (unsigned)id < table_size;
-                        const unsigned voters = __ballot_sync(0xffffffffu, valid);
-                        if (voters != 0u && valid) {
-                            // lanes holding the same id: one group, its sums by REDUX, one leader
-                            const unsigned peers = __match_any_sync(voters, (unsigned)id);
-                            const unsigned sz = __reduce_add_sync(peers, p.z);
-                            const unsigned sy = __reduce_add_sync(peers, p.y);
-                            const unsigned sx = __reduce_add_sync(peers, p.x);
+                        if (id != 0) {
+                            if (id < 0 || (unsigned)id >= table_size) continue;      // background / out of table
+                            if (id1 == 0) id1 = id;
+                            simple &= (id == id1);
+                            ++k;
+                            sxl += pos.x + e;
+                        }
+                    }
+                    if (__all_sync(0xffffffffu, simple)) {
+                        const unsigned voters = __ballot_sync(0xffffffffu, k > 0);
+                        if (k > 0) {
+                            const unsigned peers = __match_any_sync(voters, (unsigned)id1);
+                            const unsigned cnt = __reduce_add_sync(peers, (unsigned)k);
+                            const unsigned sz = __reduce_add_sync(peers, (unsigned)k * pos.z);
+                            const unsigned sy = __reduce_add_sync(peers, (unsigned)k * pos.y);
+                            const unsigned sx = __reduce_add_sync(peers, sxl);
                             if (lane == __ffs(peers) - 1) {
-                                unsigned long long *a = acc + (size_t)id * 4;
-                                atomicAdd(a + 0, (unsigned long long)__popc(peers));
+                                unsigned long long *a = acc + (size_t)id1 * 4;
+                                atomicAdd(a + 0, (unsigned long long)cnt);
                                 atomicAdd(a + 1, (unsigned long long)sz);
                                 atomicAdd(a + 2, (unsigned long long)sy);
                                 atomicAdd(a + 3, (unsigned long long)sx);
                             }
                         }
-                        if (++p.x >= (unsigned)nx) { p.x = 0; if (++p.y >= (unsigned)ny) { p.y = 0; ++p.z; } }
+                    } else {
+                        PmVox p = pos;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int id = ids[u][e];
+                            const bool valid = id > 0 && (unsigned)id < table_size;
+                            const unsigned voters = __ballot_sync(0xffffffffu, valid);
+                            if (voters != 0u && valid) {
+                                // lanes holding the same id: one group, its sums by REDUX, one leader
+                                const unsigned peers = __match_any_sync(voters, (unsigned)id);
+                                const unsigned sz = __reduce_add_sync(peers, p.z);
+                                const unsigned sy = __reduce_add_sync(peers, p.y);
+                                const unsigned sx = __reduce_add_sync(peers, p.x);
+                                if (lane == __ffs(peers) - 1) {
+                                    unsigned long long *a = acc + (size_t)id * 4;
+                                    atomicAdd(a + 0, (unsigned long long)__popc(peers));
+                                    atomicAdd(a + 1, (unsigned long long)sz);
+                                    atomicAdd(a + 2, (unsigned long long)sy);
+                                    atomicAdd(a + 3, (unsigned long long)sx);
+                                }
+                            }
+                            if (++p.x >= (unsigned)nx) { p.x = 0; if (++p.y >= (unsigned)ny) { p.y = 0; ++p.z; } }
+                        }
                     }
                 }
                 pm_vox_advance(pos, step, (unsigned)ny, (unsigned)nx);
