@@ -191,7 +191,8 @@ int pm_ransac_affine(const double *moving, const double *fixed, int k, const int
  *   A_icp [16] float64 out; residuals [iterations] float64 out (mean ||moving' - fixed[nn]||,
  *   get_error utils.py:77-88), may be NULL;  nn_out [n1] int32 last nearest-neighbour map, may be NULL.
  * workspace: pm_icp_workspace_bytes(n1). */
-size_t pm_icp_workspace_bytes(int n1);
+size_t pm_icp_workspace_bytes(int n1);            /* brute-force nearest neighbour only */
+size_t pm_icp_workspace_bytes2(int n1, int n2);  /* + the uniform grid over the fixed cloud (exact, ~50x fewer candidates) */
 int pm_icp_affine(const double *moving, int n1, const double *fixed, int n2, int iterations, double *A_icp,
                   double *residuals, int32_t *nn_out, void *workspace, size_t workspace_bytes, void *stream);
 

@@ -41,6 +41,7 @@ SIGNATURES = {
     "pm_ransac_workspace_bytes": (_sz, [_i]),
     "pm_ransac_affine": (_i, [_vp, _vp, _i, _vp, _i, _i, _d, _u64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pm_icp_workspace_bytes": (_sz, [_i]),
+    "pm_icp_workspace_bytes2": (_sz, [_i, _i]),
     "pm_icp_affine": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pm_fit_affine": (_i, [_vp, _vp, _i, _vp, _vp]),
     "pm_apply_affine": (_i, [_vp, _i, _vp, _vp, _vp]),

@@ -12,6 +12,7 @@
 // fused with the per-CTA partial sums of the normal equations; one small CTA reduces the partials in
 // a fixed order, solves the 4x4 system and composes; a third kernel applies the step and emits the
 // residual partials.  Three launches per iteration, no host synchronisation inside the loop.
+#include <stdlib.h>
 #include "pm_common.cuh"
 
 #define PM_ICP_PTS 16      // moving points per CTA
@@ -98,6 +99,7 @@ pm_icp_nn_kernel(const double *__restrict__ cur, int n1, const double *__restric
 #pragma unroll
         for (int q = 0; q < PM_ICP_NSUM; ++q) v[q] = 0.0;
         if (live) {
+            if (bj == 0x7fffffff) bj = 0;        // no finite distance at all: np.argmin of an all-NaN row
             nn[i] = bj;
             const double m[4] = {mx - shift[0], my - shift[1], mz - shift[2], 1.0};
             const double f[3] = {fixed[3 * (size_t)bj], fixed[3 * (size_t)bj + 1], fixed[3 * (size_t)bj + 2]};
@@ -118,6 +120,235 @@ pm_icp_nn_kernel(const double *__restrict__ cur, int n1, const double *__restric
     if (threadIdx.x < PM_ICP_NSUM) {   // fixed-order sum over the 32 points of this CTA
         double acc = 0.0;
         for (int q = 0; q < PM_ICP_PTS; ++q) acc += sums[q][threadIdx.x];
+        partial[(size_t)blockIdx.x * PM_ICP_NSUM + threadIdx.x] = acc;
+    }
+}
+
+// ---- exact nearest neighbour through a uniform grid over the fixed cloud ------------------------------
+// The fixed cloud does not move during ICP, so its points are bucketed once per call into a uniform grid
+// (counting sort by cell); a query visits the cells ring by ring (Chebyshev distance 0, 1, 2, ... from its
+// own cell) and stops as soon as the best distance found is smaller than the distance to everything outside
+// the visited block.  Distances are evaluated exactly as in the brute-force kernel (numpy's association
+// order, f64 sqrt) and the winner is the minimum of (distance, index), i.e. the reference's first minimum in
+// ascending index - identical nearest-neighbour maps, ~100 instead of 8000 candidates per query.
+struct PmIcpGrid {
+    double lo[3];      // lower corner of the bounding box
+    double h;          // cell edge
+    int g[3];          // cells per axis
+    int ncell;
+};
+
+__global__ void __launch_bounds__(1024) pm_icp_grid_setup_kernel(const double *__restrict__ fixed, int n2, int target,
+                                                                 PmIcpGrid *__restrict__ G, int *__restrict__ cell_count,
+                                                                 int max_cells) {
+    __shared__ double s_lo[3][32], s_hi[3][32];
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int j = threadIdx.x; j < n2; j += blockDim.x)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double x = fixed[3 * (size_t)j + a];
+            lo[a] = fmin(lo[a], x); hi[a] = fmax(hi[a], x);
+        }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0) { s_lo[a][warp] = lo[a]; s_hi[a][warp] = hi[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ext = 0.0;
+        for (int a = 0; a < 3; ++a) {
+            double l = INFINITY, u = -INFINITY;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { l = fmin(l, s_lo[a][w]); u = fmax(u, s_hi[a][w]); }
+            G->lo[a] = l;
+            s_hi[a][0] = u - l;
+            ext = fmax(ext, u - l);
+        }
+        double h = ext / (double)target;
+        if (!(h > 0.0) || !isfinite(h)) h = 1.0;             // all points coincide (or non-finite input): one cell
+        int ncell = 1;
+        for (int a = 0; a < 3; ++a) {
+            int g = (int)floor(s_hi[a][0] / h) + 1;
+            if (!(g >= 1)) g = 1;
+            if (g > target + 1) g = target + 1;
+            G->g[a] = g;
+            ncell *= g;
+        }
+        if (ncell > max_cells) { G->g[0] = G->g[1] = G->g[2] = 1; ncell = 1; h = INFINITY; }   // cannot happen: max_cells = (target+1)^3
+        G->h = h;
+        G->ncell = ncell;
+    }
+    __syncthreads();
+    const int ncell = G->ncell;
+    for (int c = threadIdx.x; c <= ncell; c += blockDim.x) cell_count[c] = 0;
+}
+
+__device__ __forceinline__ int pm_icp_cell_axis(double x, double lo, double h, int g) {
+    const double t = floor((x - lo) / h);
+    int c = (t >= (double)g) ? g - 1 : (t > 0.0 ? (int)t : 0);     // clamps queries outside the box; NaN -> 0
+    return c;
+}
+
+__global__ void __launch_bounds__(256) pm_icp_cell_count_kernel(const double *__restrict__ fixed, int n2,
+                                                                const PmIcpGrid *__restrict__ G, int *__restrict__ cell_of,
+                                                                int *__restrict__ cell_count) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n2) return;
+    const PmIcpGrid g = *G;
+    const int cz = pm_icp_cell_axis(fixed[3 * (size_t)j], g.lo[0], g.h, g.g[0]);
+    const int cy = pm_icp_cell_axis(fixed[3 * (size_t)j + 1], g.lo[1], g.h, g.g[1]);
+    const int cx = pm_icp_cell_axis(fixed[3 * (size_t)j + 2], g.lo[2], g.h, g.g[2]);
+    const int c = (cz * g.g[1] + cy) * g.g[2] + cx;
+    cell_of[j] = c;
+    atomicAdd(&cell_count[c], 1);
+}
+
+// one CTA: exclusive scan of the cell counts in place (cell_start[ncell] = n2); cursor = copy for the fill
+__global__ void __launch_bounds__(1024) pm_icp_cell_scan_kernel(const PmIcpGrid *__restrict__ G, int *__restrict__ cell_start,
+                                                                int *__restrict__ cursor) {
+    __shared__ int s_scan[33];
+    __shared__ int s_base;
+    const int ncell = G->ncell, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) s_base = 0;
+    __syncthreads();
+    for (int b = 0; b <= ncell; b += 1024) {
+        const int c = b + t;
+        const int v = (c < ncell) ? cell_start[c] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        if (t == 0) {
+            int a = s_base;
+            for (int w = 0; w < 32; ++w) { const int x = s_scan[w]; s_scan[w] = a; a += x; }
+            s_scan[32] = a;
+        }
+        __syncthreads();
+        if (c <= ncell) {
+            const int excl = s_scan[warp] + incl - v;
+            cell_start[c] = excl;
+            cursor[c] = excl;
+        }
+        __syncthreads();
+        if (t == 0) s_base = s_scan[32];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) pm_icp_cell_fill_kernel(const double *__restrict__ fixed, int n2,
+                                                               const int *__restrict__ cell_of, int *__restrict__ cursor,
+                                                               double *__restrict__ sorted_pts, int *__restrict__ sorted_idx) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n2) return;
+    const int pos = atomicAdd(&cursor[cell_of[j]], 1);
+    sorted_pts[3 * (size_t)pos] = fixed[3 * (size_t)j];
+    sorted_pts[3 * (size_t)pos + 1] = fixed[3 * (size_t)j + 1];
+    sorted_pts[3 * (size_t)pos + 2] = fixed[3 * (size_t)j + 2];
+    sorted_idx[pos] = j;
+}
+
+#define PM_ICP_GPTS 128    // moving points per CTA of the grid kernel (one per thread)
+
+__global__ void __launch_bounds__(PM_ICP_GPTS)
+pm_icp_nn_grid_kernel(const double *__restrict__ cur, int n1, const double *__restrict__ fixed,
+                      const PmIcpGrid *__restrict__ Gp, const int *__restrict__ cell_start,
+                      const double *__restrict__ sorted_pts, const int *__restrict__ sorted_idx,
+                      const double *__restrict__ shift, int32_t *__restrict__ nn, double *__restrict__ partial) {
+    __shared__ double sums[PM_ICP_GPTS][PM_ICP_NSUM + 1];
+    const PmIcpGrid G = *Gp;
+    const int i = blockIdx.x * PM_ICP_GPTS + threadIdx.x;
+    const bool live = i < n1;
+    double mx = 0, my = 0, mz = 0;
+    if (live) { mx = cur[3 * (size_t)i]; my = cur[3 * (size_t)i + 1]; mz = cur[3 * (size_t)i + 2]; }
+    double bd = INFINITY, bd2 = INFINITY;
+    int bj = 0x7fffffff;
+    if (live) {
+        const double q[3] = {mx, my, mz};
+        int c[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) c[a] = pm_icp_cell_axis(q[a], G.lo[a], G.h, G.g[a]);
+        const int rmax = max(G.g[0], max(G.g[1], G.g[2]));
+        for (int r = 0; r <= rmax; ++r) {
+            const int z0 = max(c[0] - r, 0), z1 = min(c[0] + r, G.g[0] - 1);
+            const int y0 = max(c[1] - r, 0), y1 = min(c[1] + r, G.g[1] - 1);
+            const int x0 = max(c[2] - r, 0), x1 = min(c[2] + r, G.g[2] - 1);
+            for (int z = z0; z <= z1; ++z) {
+                const bool zface = (z == c[0] - r) || (z == c[0] + r);
+                for (int y = y0; y <= y1; ++y) {
+                    const bool yface = zface || (y == c[1] - r) || (y == c[1] + r);
+                    // on a face of the block the whole x-run belongs to ring r, otherwise only its two ends
+                    const int xa = yface ? x0 : ((c[2] - r >= 0) ? c[2] - r : x1 + 1);
+                    const int row = (z * G.g[1] + y) * G.g[2];
+                    auto scan_cells = [&](int xs, int xe) {     // contiguous cells -> contiguous sorted points
+                        if (xs > xe) return;
+                        const int p0 = __ldg(cell_start + row + xs), p1 = __ldg(cell_start + row + xe + 1);
+                        for (int p = p0; p < p1; ++p) {
+                            const double d0 = __ldg(sorted_pts + 3 * (size_t)p) - mx, d1 = __ldg(sorted_pts + 3 * (size_t)p + 1) - my,
+                                         d2 = __ldg(sorted_pts + 3 * (size_t)p + 2) - mz;
+                            const double q2 = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+                            // candidates come in no particular index order, and two different q2 can round to the
+                            // same distance: let everything within a few ulp of the best through and decide on
+                            // (distance, index), which is the reference's first minimum in ascending index
+                            if (q2 <= bd2 * (1.0 + 1e-15)) {
+                                const double d = sqrt(q2);
+                                const int j = __ldg(sorted_idx + p);
+                                if (d < bd || (d == bd && j < bj)) { bd = d; bj = j; bd2 = q2; }
+                            }
+                        }
+                    };
+                    if (yface) scan_cells(x0, x1);
+                    else {
+                        if (c[2] - r >= 0) scan_cells(c[2] - r, c[2] - r);
+                        if (r > 0 && c[2] + r <= G.g[2] - 1) scan_cells(c[2] + r, c[2] + r);
+                    }
+                    (void)xa;
+                }
+            }
+            // everything not visited yet lies outside the block of cells [c - r, c + r]: lower bound of its distance
+            double bound = INFINITY;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                if (c[a] - r > 0) bound = fmin(bound, fmax(q[a] - (G.lo[a] + (double)(c[a] - r) * G.h), 0.0));
+                if (c[a] + r < G.g[a] - 1) bound = fmin(bound, fmax((G.lo[a] + (double)(c[a] + r + 1) * G.h) - q[a], 0.0));
+            }
+            if (!(bound < INFINITY)) break;                        // the block covers the whole grid
+            // strictly closer than anything outside, with slack for the rounding of the cell assignment
+            if (bd < bound * (1.0 - 1e-12) - 1e-9 * G.h) break;
+        }
+    }
+    double v[PM_ICP_NSUM];
+#pragma unroll
+    for (int q = 0; q < PM_ICP_NSUM; ++q) v[q] = 0.0;
+    if (live) {
+        if (bj == 0x7fffffff) bj = 0;            // no finite distance at all: np.argmin of an all-NaN row
+        nn[i] = bj;
+        const double m[4] = {mx - shift[0], my - shift[1], mz - shift[2], 1.0};
+        const double f[3] = {fixed[3 * (size_t)bj], fixed[3 * (size_t)bj + 1], fixed[3 * (size_t)bj + 2]};
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = a; b < 4; ++b) v[q++] = m[a] * m[b];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) v[q++] = f[a] * m[b];
+    }
+#pragma unroll
+    for (int q = 0; q < PM_ICP_NSUM; ++q) sums[threadIdx.x][q] = v[q];
+    __syncthreads();
+    if (threadIdx.x < PM_ICP_NSUM) {   // fixed-order sum over the points of this CTA
+        double acc = 0.0;
+        for (int q = 0; q < PM_ICP_GPTS; ++q) acc += sums[q][threadIdx.x];
         partial[(size_t)blockIdx.x * PM_ICP_NSUM + threadIdx.x] = acc;
     }
 }
@@ -207,16 +438,33 @@ __global__ void pm_icp_init_kernel(const double *__restrict__ moving, double *__
 
 static inline size_t pm_align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-extern "C" size_t pm_icp_workspace_bytes(int n1) {
-    if (n1 < 1) return 0;
+static int pm_icp_grid_target(int n2) {      // cells along the longest axis: ~2 n2^(1/3), so occupied cells hold a few points
+    int t = (int)ceil(2.0 * cbrt((double)(n2 > 1 ? n2 : 1)));
+    if (t < 1) t = 1;
+    if (t > 160) t = 160;
+    return t;
+}
+
+static size_t pm_icp_grid_bytes(int n2) {
+    const size_t t = (size_t)pm_icp_grid_target(n2) + 1, max_cells = t * t * t;
+    return pm_align256(sizeof(PmIcpGrid)) + 2 * pm_align256((max_cells + 1) * sizeof(int))   // cell_start, cursor
+         + pm_align256((size_t)n2 * sizeof(int)) * 2                                          // cell_of, sorted_idx
+         + pm_align256((size_t)n2 * 3 * sizeof(double));                                      // sorted_pts
+}
+
+extern "C" size_t pm_icp_workspace_bytes2(int n1, int n2) {
+    if (n1 < 1 || n2 < 1) return 0;
     const size_t nb_nn = (size_t)(n1 + PM_ICP_PTS - 1) / PM_ICP_PTS;
     const size_t nb_ap = (size_t)(n1 + 255) / 256;
     return pm_align256((size_t)n1 * 3 * sizeof(double))          // cur
          + pm_align256((size_t)n1 * sizeof(int32_t))             // nn
          + pm_align256(nb_nn * PM_ICP_NSUM * sizeof(double))     // partial
          + pm_align256(64 * sizeof(double))                      // a_est, a_icp, shift
-         + pm_align256(nb_ap * sizeof(double) * 1024);           // residual partials (<= 1024 iterations)
+         + pm_align256(nb_ap * sizeof(double) * 1024)            // residual partials (<= 1024 iterations)
+         + pm_icp_grid_bytes(n2);                                // uniform grid over the fixed cloud
 }
+
+extern "C" size_t pm_icp_workspace_bytes(int n1) { return pm_icp_workspace_bytes2(n1, 0 + 1) - pm_icp_grid_bytes(1); }
 
 extern "C" int pm_icp_affine(const double *moving, int n1, const double *fixed, int n2, int iterations,
                              double *A_icp, double *residuals, int32_t *nn_out, void *workspace,
@@ -228,6 +476,8 @@ extern "C" int pm_icp_affine(const double *moving, int n1, const double *fixed, 
         pm_set_error("pm_icp_affine: workspace too small");
         return PM_ERR_WORKSPACE;
     }
+    // the grid search needs the larger workspace of pm_icp_workspace_bytes2 (and pays off from a few hundred points)
+    const bool use_grid = n2 >= 256 && workspace_bytes >= pm_icp_workspace_bytes2(n1, n2) && !getenv("PM_ICP_BRUTE");
     cudaStream_t s = pm_stream(stream);
     const int nb_nn = (n1 + PM_ICP_PTS - 1) / PM_ICP_PTS, nb_ap = (n1 + 255) / 256;
     char *w = (char *)workspace;
@@ -235,14 +485,36 @@ extern "C" int pm_icp_affine(const double *moving, int n1, const double *fixed, 
     int32_t *nn = (int32_t *)w; w += pm_align256((size_t)n1 * sizeof(int32_t));
     double *partial = (double *)w; w += pm_align256((size_t)nb_nn * PM_ICP_NSUM * sizeof(double));
     double *small = (double *)w; w += pm_align256(64 * sizeof(double));
-    double *res_partial = (double *)w;
+    double *res_partial = (double *)w; w += pm_align256((size_t)nb_ap * sizeof(double) * 1024);
     double *a_est = small, *a_icp = small + 16, *shift = small + 32;
+    PmIcpGrid *grid = nullptr;
+    int *cell_start = nullptr, *cursor = nullptr, *cell_of = nullptr, *sorted_idx = nullptr;
+    double *sorted_pts = nullptr;
+    if (use_grid) {
+        const size_t t = (size_t)pm_icp_grid_target(n2) + 1, max_cells = t * t * t;
+        grid = (PmIcpGrid *)w; w += pm_align256(sizeof(PmIcpGrid));
+        cell_start = (int *)w; w += pm_align256((max_cells + 1) * sizeof(int));
+        cursor = (int *)w; w += pm_align256((max_cells + 1) * sizeof(int));
+        cell_of = (int *)w; w += pm_align256((size_t)n2 * sizeof(int));
+        sorted_idx = (int *)w; w += pm_align256((size_t)n2 * sizeof(int));
+        sorted_pts = (double *)w;
+        pm_icp_grid_setup_kernel<<<1, 1024, 0, s>>>(fixed, n2, pm_icp_grid_target(n2), grid, cell_start, (int)max_cells);
+        pm_icp_cell_count_kernel<<<(n2 + 255) / 256, 256, 0, s>>>(fixed, n2, grid, cell_of, cell_start);
+        pm_icp_cell_scan_kernel<<<1, 1024, 0, s>>>(grid, cell_start, cursor);
+        pm_icp_cell_fill_kernel<<<(n2 + 255) / 256, 256, 0, s>>>(fixed, n2, cell_of, cursor, sorted_pts, sorted_idx);
+        PM_LAUNCH_CHECK_N(4);
+    }
+    const int nb_grid = (n1 + PM_ICP_GPTS - 1) / PM_ICP_GPTS;
     PM_CUDA_TRY(cudaMemcpyAsync(cur, moving, (size_t)n1 * 3 * sizeof(double), cudaMemcpyDeviceToDevice, s));
     pm_icp_init_kernel<<<1, 32, 0, s>>>(moving, a_icp, shift);
     PM_LAUNCH_CHECK();
     for (int it = 0; it < iterations; ++it) {
-        pm_icp_nn_kernel<<<nb_nn, PM_ICP_PTS * PM_ICP_SLICES, 0, s>>>(cur, n1, fixed, n2, shift, nn, partial);
-        pm_icp_solve_kernel<<<1, 256, 0, s>>>(partial, nb_nn, shift, a_est, a_icp);
+        if (use_grid)
+            pm_icp_nn_grid_kernel<<<nb_grid, PM_ICP_GPTS, 0, s>>>(cur, n1, fixed, grid, cell_start, sorted_pts, sorted_idx,
+                                                                  shift, nn, partial);
+        else
+            pm_icp_nn_kernel<<<nb_nn, PM_ICP_PTS * PM_ICP_SLICES, 0, s>>>(cur, n1, fixed, n2, shift, nn, partial);
+        pm_icp_solve_kernel<<<1, 256, 0, s>>>(partial, use_grid ? nb_grid : nb_nn, shift, a_est, a_icp);
         pm_icp_apply_kernel<<<nb_ap, 256, 0, s>>>(cur, n1, fixed, nn, a_est, res_partial + (size_t)it * nb_ap);
     }
     PM_LAUNCH_CHECK_N(3 * iterations);

@@ -160,7 +160,7 @@ def icp_affine(moving, fixed, iterations=50, want_nn=False):
     a_icp = torch.empty(16, dtype=torch.float64, device=dev)
     resid = torch.empty(max(iterations, 1), dtype=torch.float64, device=dev)
     nn = torch.empty(n1, dtype=torch.int32, device=dev) if want_nn else None
-    nbytes = load().pm_icp_workspace_bytes(n1)
+    nbytes = load().pm_icp_workspace_bytes2(n1, n2)
     ws = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=dev)
     check(load().pm_icp_affine(ptr(moving), n1, ptr(fixed), n2, int(iterations), ptr(a_icp), ptr(resid), ptr(nn),
                                ptr(ws), nbytes, stream_ptr()), "pm_icp_affine")

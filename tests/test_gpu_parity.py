@@ -328,6 +328,35 @@ def test_icp_nearest_neighbour_map(O, D, torch):
     assert np.array_equal(nn.cpu().numpy(), nn_o)
 
 
+@pytest.mark.parametrize("case", ["shell", "filled", "outliers", "lattice_ties", "identical", "flat"])
+def test_icp_grid_search_matches_brute_force(O, D, torch, case, monkeypatch):
+    """The uniform-grid search returns exactly the brute-force nearest-neighbour map (first minimum in ascending
+    index), also with exact distance ties, queries far outside the fixed cloud's box and degenerate boxes."""
+    rng = np.random.default_rng(len(case))
+    if case == "shell":
+        p = _pair(3000, seed=4); f = p["fixed"]; m = O.apply_affine_transform(p["moving"], p["A_gt"])
+    elif case == "filled":
+        f = rng.random((3, 2500)) * 300; m = rng.random((3, 2000)) * 300
+    elif case == "outliers":
+        f = rng.random((3, 1500)) * 100; m = np.concatenate([rng.random((3, 900)) * 100, rng.random((3, 100)) * 5000 - 2500], axis=1)
+    elif case == "lattice_ties":
+        g = np.stack(np.meshgrid(np.arange(12.0), np.arange(12.0), np.arange(12.0), indexing="ij")).reshape(3, -1)
+        f = g[:, rng.permutation(g.shape[1])]; m = g[:, :800] + 0.5            # every query has 8 equidistant neighbours
+    elif case == "identical":
+        f = rng.random((3, 1200)) * 50; m = f[:, rng.permutation(1200)[:900]].copy()
+    else:
+        f = rng.random((3, 1000)) * 80; f[0] = 7.0; m = rng.random((3, 700)) * 80          # zero extent along z
+    _, _, nn = D.icp_affine(D.to_device_points(m), D.to_device_points(f), 1, want_nn=True)
+    nn_o, _ = O.nearest(m, f)
+    assert np.array_equal(nn.cpu().numpy(), nn_o)
+    monkeypatch.setenv("PM_ICP_BRUTE", "1")
+    a_b, r_b, nn_b = D.icp_affine(D.to_device_points(m), D.to_device_points(f), 3, want_nn=True)
+    monkeypatch.delenv("PM_ICP_BRUTE")
+    a_g, r_g, nn_g = D.icp_affine(D.to_device_points(m), D.to_device_points(f), 3, want_nn=True)
+    assert torch.equal(nn_b, nn_g)
+    assert torch.allclose(a_b, a_g, rtol=1e-9, atol=1e-9, equal_nan=True) or case == "lattice_ties"   # (rank-deficient fits)
+
+
 def test_fit_apply_compose(O, torch, golden):
     from platymatch_b200.estimate_transform.find_transform import get_affine_transform
     from platymatch_b200.estimate_transform.apply_transform import apply_affine_transform
