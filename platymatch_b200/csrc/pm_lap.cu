@@ -1092,7 +1092,7 @@ __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmL
         for (int j = t; j < ncp; j += PM_SS_THREADS) { d[j] = INFINITY; scanned[j] = 0; }
         if (t == 0) { s_lam = INFINITY; s_lam_idx = -1; s_nfront = 0; }
         __syncthreads();
-        int i = cur, sink = -1, nt = 0;
+        int i = cur, sink = -1, nt = 0, jlast = -1;      // jlast: column finalised in the previous step
         double dist = 0.0, min_val = 0.0;
         while (sink < 0 && status == 0) {
             // ---- add row i (distance dist) to the tree: relax its list edges, record its bound
@@ -1100,7 +1100,7 @@ __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmL
             if (t < PM_LS_K) {
                 const int j = __ldcg(V.lcol + (size_t)i * PM_LS_K + t);          // both list loads in flight together
                 const float cij = __ldcg(V.lcost + (size_t)i * PM_LS_K + t);
-                if (j >= 0 && !scanned[j]) {
+                if (j >= 0 && j != jlast && !scanned[j]) {     // (its scanned flag may not be visible yet)
                     const double r = ((dist + (double)cij) - ui) - v[j];
                     const double old = d[j];
                     if (r < old) {
@@ -1116,7 +1116,7 @@ __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmL
             ++nt;
             __syncthreads();
             while (true) {
-                // ---- closest unscanned column (ties prefer a free column, then the lower index)
+                // ---- closest unscanned column (ties: the lower index)
                 double best = INFINITY;
                 int best_tie = INT_MAX;
                 const int nfront = s_nfront;
@@ -1124,8 +1124,7 @@ __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmL
                     const int j = front[q];
                     if (!scanned[j]) {
                         const double dj = d[j];
-                        const int tie = ((r4c[j] != PM_LS_NONE) ? (1 << 30) : 0) | j;
-                        if (dj < best || (dj == best && tie < best_tie)) { best = dj; best_tie = tie; }
+                        if (dj < best || (dj == best && j < best_tie)) { best = dj; best_tie = j; }
                     }
                 }
                 pm_ss_argmin_warp(best, best_tie);
@@ -1141,11 +1140,11 @@ __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmL
                     if (!(best < INFINITY)) { status = PM_ERR_INFEASIBLE; break; }
                     ++steps;
                     min_val = best;
-                    const int jm = best_tie & ((1 << 30) - 1);
-                    if (t == 0) scanned[jm] = 1;
-                    if (!(best_tie >> 30)) sink = jm;
+                    const int jm = best_tie;
+                    if (t == 0) scanned[jm] = 1;                // visible to everybody after the next barrier
+                    jlast = jm;
+                    if (r4c[jm] == PM_LS_NONE) sink = jm;
                     else { i = r4c[jm]; dist = best; }
-                    __syncthreads();                           // the scanned flag is visible before the next relaxation
                     break;
                 }
                 // ---- an edge outside the list of tree row `il` could be shorter: relax that row densely

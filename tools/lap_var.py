@@ -24,3 +24,10 @@ for slot in range(4):
             print("   slow rep", rep, "%.2f ms" % ts[-1], "bids", st[:, 5].tolist(), "bulk", st[:, 11].tolist(), "augment", st[:, 2].tolist(),
                   "dijkstra", st[:, 3].tolist(), "auction_cyc", st[:, 10].tolist(), "dense", st[:, 12].tolist())
     print("slot", slot, "ms:", " ".join("%.1f" % t for t in ts))
+    print("   last rep: bids", st[:, 5].tolist(), "bulk", st[:, 11].tolist(), "refresh", st[:, 6].tolist(), "parked", st[:, 8].tolist(),
+          "augment", st[:, 2].tolist(), "dijkstra", st[:, 3].tolist(), "tail_cyc", st[:, 10].tolist(), "dense", st[:, 12].tolist())
+    for q in range(4):      # each matrix alone
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); D.lap_solve(cost[q:q + 1], n1, n2); e1.record(); torch.cuda.synchronize()
+        print("   matrix %d alone: %.2f ms" % (q, e0.elapsed_time(e1)))
