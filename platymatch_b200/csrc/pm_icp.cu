@@ -13,7 +13,10 @@
 // a fixed order, solves the 4x4 system and composes; a third kernel applies the step and emits the
 // residual partials.  Three launches per iteration, no host synchronisation inside the loop.
 #include <stdlib.h>
+#include <cooperative_groups.h>
 #include "pm_common.cuh"
+
+namespace cg = cooperative_groups;
 
 #define PM_ICP_PTS 16      // moving points per CTA
 #define PM_ICP_SLICES 16   // column slices per moving point (threads = 16 x 16)
@@ -257,21 +260,22 @@ __global__ void __launch_bounds__(256) pm_icp_cell_fill_kernel(const double *__r
 }
 
 #define PM_ICP_GPTS 128    // moving points per CTA of the grid kernel (one per thread)
+#define PM_ICP_QPB 32      // persistent kernel: moving points per CTA ...
+#define PM_ICP_LPQ 4       // ... and lanes that share the candidates of one point
 
-__global__ void __launch_bounds__(PM_ICP_GPTS)
-pm_icp_nn_grid_kernel(const double *__restrict__ cur, int n1, const double *__restrict__ fixed,
-                      const PmIcpGrid *__restrict__ Gp, const int *__restrict__ cell_start,
-                      const double *__restrict__ sorted_pts, const int *__restrict__ sorted_idx,
-                      const double *__restrict__ shift, int32_t *__restrict__ nn, double *__restrict__ partial) {
-    __shared__ double sums[PM_ICP_GPTS][PM_ICP_NSUM + 1];
-    const PmIcpGrid G = *Gp;
-    const int i = blockIdx.x * PM_ICP_GPTS + threadIdx.x;
-    const bool live = i < n1;
-    double mx = 0, my = 0, mz = 0;
-    if (live) { mx = cur[3 * (size_t)i]; my = cur[3 * (size_t)i + 1]; mz = cur[3 * (size_t)i + 2]; }
-    double bd = INFINITY, bd2 = INFINITY;
-    int bj = 0x7fffffff;
-    if (live) {
+// nearest fixed point of (mx, my, mz): ring-by-ring search of the grid, winner = min (distance, index)
+// NSUB adjacent lanes share one query: each takes every NSUB-th candidate of a cell run and the partial
+// winners are merged with shuffles after every ring (all NSUB lanes leave with the same result).
+template <int NSUB>
+__device__ __forceinline__ void pm_icp_grid_search(const PmIcpGrid &G, const int *__restrict__ cell_start,
+                                                   const double *__restrict__ sorted_pts, const int *__restrict__ sorted_idx,
+                                                   double mx, double my, double mz, double &bd, int &bj) {
+    const int sub = (NSUB > 1) ? (threadIdx.x & (NSUB - 1)) : 0;
+    // the lanes of one query run in lockstep, different queries of a warp do not: shuffle within the group only
+    const unsigned gmask = (NSUB > 1) ? (((1u << NSUB) - 1u) << ((threadIdx.x & 31) & ~(NSUB - 1))) : 0u;
+    double bd2 = INFINITY;
+    bd = INFINITY;
+    bj = 0x7fffffff;
         const double q[3] = {mx, my, mz};
         int c[3];
 #pragma unroll
@@ -291,7 +295,7 @@ pm_icp_nn_grid_kernel(const double *__restrict__ cur, int n1, const double *__re
                     auto scan_cells = [&](int xs, int xe) {     // contiguous cells -> contiguous sorted points
                         if (xs > xe) return;
                         const int p0 = __ldg(cell_start + row + xs), p1 = __ldg(cell_start + row + xe + 1);
-                        for (int p = p0; p < p1; ++p) {
+                        for (int p = p0 + sub; p < p1; p += NSUB) {
                             const double d0 = __ldg(sorted_pts + 3 * (size_t)p) - mx, d1 = __ldg(sorted_pts + 3 * (size_t)p + 1) - my,
                                          d2 = __ldg(sorted_pts + 3 * (size_t)p + 2) - mz;
                             const double q2 = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
@@ -313,6 +317,14 @@ pm_icp_nn_grid_kernel(const double *__restrict__ cur, int n1, const double *__re
                     (void)xa;
                 }
             }
+            if (NSUB > 1) {     // merge the lanes of this query: minimum of (distance, index)
+#pragma unroll
+                for (int o = 1; o < NSUB; o <<= 1) {
+                    const double od = __shfl_xor_sync(gmask, bd, o), o2 = __shfl_xor_sync(gmask, bd2, o);
+                    const int oj = __shfl_xor_sync(gmask, bj, o);
+                    if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; bd2 = o2; }
+                }
+            }
             // everything not visited yet lies outside the block of cells [c - r, c + r]: lower bound of its distance
             double bound = INFINITY;
 #pragma unroll
@@ -324,7 +336,56 @@ pm_icp_nn_grid_kernel(const double *__restrict__ cur, int n1, const double *__re
             // strictly closer than anything outside, with slack for the rounding of the cell assignment
             if (bd < bound * (1.0 - 1e-12) - 1e-9 * G.h) break;
         }
+}
+
+// normal-equation terms of one correspondence: 10 (M M^T upper) + 12 (F M^T)
+__device__ __forceinline__ void pm_icp_terms(double mx, double my, double mz, const double *__restrict__ shift,
+                                             const double *__restrict__ fixed, int bj, double v[PM_ICP_NSUM]) {
+    const double m[4] = {mx - shift[0], my - shift[1], mz - shift[2], 1.0};
+    const double f[3] = {fixed[3 * (size_t)bj], fixed[3 * (size_t)bj + 1], fixed[3 * (size_t)bj + 2]};
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = a; b < 4; ++b) v[q++] = m[a] * m[b];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) v[q++] = f[a] * m[b];
+}
+
+// A_est (4x4, row-major) from the 22 summed terms; NaN rows when the moving points are rank deficient
+__device__ inline void pm_icp_solve_terms(const double *tot, const double *__restrict__ shift, double A[16]) {
+    double M[16], X[12];
+    int k = 0;
+    for (int a = 0; a < 4; ++a)
+        for (int b = a; b < 4; ++b) { M[a * 4 + b] = tot[k]; M[b * 4 + a] = tot[k]; ++k; }
+    const bool ok = pm_solve_right_4x4(M, tot + 10, 3, X, 1e-14);
+    for (int r = 0; r < 3; ++r) {
+        if (ok) {
+            A[r * 4 + 0] = X[r * 4 + 0]; A[r * 4 + 1] = X[r * 4 + 1]; A[r * 4 + 2] = X[r * 4 + 2];
+            A[r * 4 + 3] = X[r * 4 + 3] - (X[r * 4 + 0] * shift[0] + X[r * 4 + 1] * shift[1] + X[r * 4 + 2] * shift[2]);
+        } else {
+            for (int c = 0; c < 4; ++c) A[r * 4 + c] = nan("");
+        }
     }
+    A[12] = 0.0; A[13] = 0.0; A[14] = 0.0; A[15] = 1.0;
+}
+
+__global__ void __launch_bounds__(PM_ICP_GPTS)
+pm_icp_nn_grid_kernel(const double *__restrict__ cur, int n1, const double *__restrict__ fixed,
+                      const PmIcpGrid *__restrict__ Gp, const int *__restrict__ cell_start,
+                      const double *__restrict__ sorted_pts, const int *__restrict__ sorted_idx,
+                      const double *__restrict__ shift, int32_t *__restrict__ nn, double *__restrict__ partial) {
+    __shared__ double sums[PM_ICP_GPTS][PM_ICP_NSUM + 1];
+    const PmIcpGrid G = *Gp;
+    const int i = blockIdx.x * PM_ICP_GPTS + threadIdx.x;
+    const bool live = i < n1;
+    double mx = 0, my = 0, mz = 0;
+    if (live) { mx = cur[3 * (size_t)i]; my = cur[3 * (size_t)i + 1]; mz = cur[3 * (size_t)i + 2]; }
+    double bd = INFINITY;
+    int bj = 0x7fffffff;
+    if (live) pm_icp_grid_search<1>(G, cell_start, sorted_pts, sorted_idx, mx, my, mz, bd, bj);
     double v[PM_ICP_NSUM];
 #pragma unroll
     for (int q = 0; q < PM_ICP_NSUM; ++q) v[q] = 0.0;
@@ -351,6 +412,94 @@ pm_icp_nn_grid_kernel(const double *__restrict__ cur, int n1, const double *__re
         for (int q = 0; q < PM_ICP_GPTS; ++q) acc += sums[q][threadIdx.x];
         partial[(size_t)blockIdx.x * PM_ICP_NSUM + threadIdx.x] = acc;
     }
+}
+
+// ---- the whole ICP loop in ONE cooperative launch -------------------------------------------------------
+// One thread per moving point keeps its point in registers for all iterations.  Per iteration: grid nearest
+// neighbour + per-CTA partial sums of the 22 normal-equation terms -> ONE grid barrier -> every CTA reduces
+// the partials in the same fixed order and solves the 4x4 system itself (redundantly: cheaper than a second
+// barrier and a broadcast) -> apply, residual partials.  The partial sums ping-pong between two buffers, so
+// a CTA that runs ahead into the next iteration cannot overwrite what a slower one still reads.
+__global__ void __launch_bounds__(PM_ICP_QPB * PM_ICP_LPQ)
+pm_icp_persistent_kernel(const double *__restrict__ moving, int n1, const double *__restrict__ fixed, int iterations,
+                         const PmIcpGrid *__restrict__ Gp, const int *__restrict__ cell_start,
+                         const double *__restrict__ sorted_pts, const int *__restrict__ sorted_idx,
+                         int32_t *__restrict__ nn, double *__restrict__ partial /* [2][grid][NSUM] */,
+                         double *__restrict__ res_partial /* [iterations][grid] */, double *__restrict__ a_icp_out) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sums[PM_ICP_QPB][PM_ICP_NSUM + 1];
+    __shared__ double tot[PM_ICP_NSUM];
+    __shared__ double s_a[16];
+    __shared__ double red[32];
+    const PmIcpGrid G = *Gp;
+    const int nblk = gridDim.x;
+    const int qi = threadIdx.x / PM_ICP_LPQ;                   // query slot of this thread; PM_ICP_LPQ lanes share it
+    const bool lead = (threadIdx.x % PM_ICP_LPQ) == 0;
+    const int i = blockIdx.x * PM_ICP_QPB + qi;
+    const bool live = i < n1;
+    const double shift[3] = {moving[0], moving[1], moving[2]};
+    double mx = 0, my = 0, mz = 0;
+    if (live) { mx = moving[3 * (size_t)i]; my = moving[3 * (size_t)i + 1]; mz = moving[3 * (size_t)i + 2]; }
+    double a_icp[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) a_icp[e] = (e % 5 == 0) ? 1.0 : 0.0;
+    for (int it = 0; it < iterations; ++it) {
+        double bd = INFINITY;
+        int bj = 0;
+        double v[PM_ICP_NSUM];
+#pragma unroll
+        for (int q = 0; q < PM_ICP_NSUM; ++q) v[q] = 0.0;
+        // (a whole group of PM_ICP_LPQ lanes is live or not: the shuffles inside stay converged)
+        pm_icp_grid_search<PM_ICP_LPQ>(G, cell_start, sorted_pts, sorted_idx, mx, my, mz, bd, bj);
+        if (live) {
+            if (bj == 0x7fffffff) bj = 0;        // no finite distance at all: np.argmin of an all-NaN row
+            pm_icp_terms(mx, my, mz, shift, fixed, bj, v);
+        }
+        if (lead) {
+#pragma unroll
+            for (int q = 0; q < PM_ICP_NSUM; ++q) sums[qi][q] = live ? v[q] : 0.0;
+        }
+        __syncthreads();
+        double *pbuf = partial + (size_t)(it & 1) * nblk * PM_ICP_NSUM;
+        if (threadIdx.x < PM_ICP_NSUM) {   // fixed-order sum over the points of this CTA
+            double acc = 0.0;
+            for (int q = 0; q < PM_ICP_QPB; ++q) acc += sums[q][threadIdx.x];
+            pbuf[(size_t)blockIdx.x * PM_ICP_NSUM + threadIdx.x] = acc;
+        }
+        grid.sync();
+        if (threadIdx.x < PM_ICP_NSUM) {   // every CTA: the same fixed-order reduction over all CTAs
+            double acc = 0.0;
+            for (int b = 0; b < nblk; ++b) acc += __ldcg(pbuf + (size_t)b * PM_ICP_NSUM + threadIdx.x);
+            tot[threadIdx.x] = acc;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) pm_icp_solve_terms(tot, shift, s_a);
+        __syncthreads();
+        double r = 0.0;
+        if (live) {     // apply (apply_transform.py:14-17), residual against this iteration's matches (utils.py:77-88)
+            const double nx = ((s_a[0] * mx + s_a[1] * my) + s_a[2] * mz) + s_a[3];
+            const double ny = ((s_a[4] * mx + s_a[5] * my) + s_a[6] * mz) + s_a[7];
+            const double nz = ((s_a[8] * mx + s_a[9] * my) + s_a[10] * mz) + s_a[11];
+            mx = nx; my = ny; mz = nz;
+            const double e0 = nx - fixed[3 * (size_t)bj], e1 = ny - fixed[3 * (size_t)bj + 1], e2 = nz - fixed[3 * (size_t)bj + 2];
+            r = lead ? sqrt(e0 * e0 + e1 * e1 + e2 * e2) : 0.0;
+            if (lead && it == iterations - 1) nn[i] = bj;
+        }
+        r = pm_block_sum(r, red);
+        if (threadIdx.x == 0) res_partial[(size_t)it * nblk + blockIdx.x] = r;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {      // A_icp <- A_est @ A_icp   (perform_icp.py:25)
+            double c[16];
+            for (int rr = 0; rr < 4; ++rr)
+                for (int cc = 0; cc < 4; ++cc) {
+                    double sacc = 0.0;
+                    for (int kk = 0; kk < 4; ++kk) sacc += s_a[rr * 4 + kk] * a_icp[kk * 4 + cc];
+                    c[rr * 4 + cc] = sacc;
+                }
+            for (int e = 0; e < 16; ++e) a_icp[e] = c[e];
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int e = 0; e < 16; ++e) a_icp_out[e] = a_icp[e];
 }
 
 // One CTA: reduce partials, solve, compose.  A_est -> a_est[16]; a_icp <- A_est @ a_icp.
@@ -455,12 +604,12 @@ static size_t pm_icp_grid_bytes(int n2) {
 extern "C" size_t pm_icp_workspace_bytes2(int n1, int n2) {
     if (n1 < 1 || n2 < 1) return 0;
     const size_t nb_nn = (size_t)(n1 + PM_ICP_PTS - 1) / PM_ICP_PTS;
-    const size_t nb_ap = (size_t)(n1 + 255) / 256;
+    const size_t nb_res = (size_t)(n1 + PM_ICP_QPB - 1) / PM_ICP_QPB;
     return pm_align256((size_t)n1 * 3 * sizeof(double))          // cur
          + pm_align256((size_t)n1 * sizeof(int32_t))             // nn
-         + pm_align256(nb_nn * PM_ICP_NSUM * sizeof(double))     // partial
+         + pm_align256((nb_nn + 2 * nb_res) * PM_ICP_NSUM * sizeof(double))     // partial (ping-pong for the persistent kernel)
          + pm_align256(64 * sizeof(double))                      // a_est, a_icp, shift
-         + pm_align256(nb_ap * sizeof(double) * 1024)            // residual partials (<= 1024 iterations)
+         + pm_align256(nb_res * sizeof(double) * 1024)           // residual partials (<= 1024 iterations)
          + pm_icp_grid_bytes(n2);                                // uniform grid over the fixed cloud
 }
 
@@ -483,9 +632,10 @@ extern "C" int pm_icp_affine(const double *moving, int n1, const double *fixed, 
     char *w = (char *)workspace;
     double *cur = (double *)w; w += pm_align256((size_t)n1 * 3 * sizeof(double));
     int32_t *nn = (int32_t *)w; w += pm_align256((size_t)n1 * sizeof(int32_t));
-    double *partial = (double *)w; w += pm_align256((size_t)nb_nn * PM_ICP_NSUM * sizeof(double));
+    const int nb_pers = (n1 + PM_ICP_QPB - 1) / PM_ICP_QPB;
+    double *partial = (double *)w; w += pm_align256((size_t)(nb_nn + 2 * nb_pers) * PM_ICP_NSUM * sizeof(double));
     double *small = (double *)w; w += pm_align256(64 * sizeof(double));
-    double *res_partial = (double *)w; w += pm_align256((size_t)nb_ap * sizeof(double) * 1024);
+    double *res_partial = (double *)w; w += pm_align256((size_t)nb_pers * sizeof(double) * 1024);
     double *a_est = small, *a_icp = small + 16, *shift = small + 32;
     PmIcpGrid *grid = nullptr;
     int *cell_start = nullptr, *cursor = nullptr, *cell_of = nullptr, *sorted_idx = nullptr;
@@ -505,6 +655,29 @@ extern "C" int pm_icp_affine(const double *moving, int n1, const double *fixed, 
         PM_LAUNCH_CHECK_N(4);
     }
     const int nb_grid = (n1 + PM_ICP_GPTS - 1) / PM_ICP_GPTS;
+    if (use_grid && iterations > 0 && !getenv("PM_ICP_MULTI_LAUNCH")) {
+        // whole loop in one cooperative launch when every CTA can be resident at once
+        int dev = 0, sms = 0, per_sm = 0;
+        PM_CUDA_TRY(cudaGetDevice(&dev));
+        PM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        PM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm_icp_persistent_kernel, PM_ICP_QPB * PM_ICP_LPQ, 0));
+        if (nb_pers <= sms * per_sm) {
+            double *a_out = a_icp;
+            void *args[] = {(void *)&moving, (void *)&n1, (void *)&fixed, (void *)&iterations, (void *)&grid, (void *)&cell_start,
+                            (void *)&sorted_pts, (void *)&sorted_idx, (void *)&nn, (void *)&partial, (void *)&res_partial,
+                            (void *)&a_out};
+            PM_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)pm_icp_persistent_kernel, dim3(nb_pers),
+                                                    dim3(PM_ICP_QPB * PM_ICP_LPQ), args, 0, s));
+            PM_LAUNCH_CHECK();
+            if (residuals) {
+                pm_icp_residual_kernel<<<iterations, 256, 0, s>>>(res_partial, nb_pers, n1, residuals);
+                PM_LAUNCH_CHECK();
+            }
+            PM_CUDA_TRY(cudaMemcpyAsync(A_icp, a_icp, 16 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            if (nn_out) PM_CUDA_TRY(cudaMemcpyAsync(nn_out, nn, (size_t)n1 * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+            return PM_OK;
+        }
+    }
     PM_CUDA_TRY(cudaMemcpyAsync(cur, moving, (size_t)n1 * 3 * sizeof(double), cudaMemcpyDeviceToDevice, s));
     pm_icp_init_kernel<<<1, 32, 0, s>>>(moving, a_icp, shift);
     PM_LAUNCH_CHECK();

@@ -352,9 +352,15 @@ def test_icp_grid_search_matches_brute_force(O, D, torch, case, monkeypatch):
     monkeypatch.setenv("PM_ICP_BRUTE", "1")
     a_b, r_b, nn_b = D.icp_affine(D.to_device_points(m), D.to_device_points(f), 3, want_nn=True)
     monkeypatch.delenv("PM_ICP_BRUTE")
+    monkeypatch.setenv("PM_ICP_MULTI_LAUNCH", "1")          # grid search, three launches per iteration
     a_g, r_g, nn_g = D.icp_affine(D.to_device_points(m), D.to_device_points(f), 3, want_nn=True)
-    assert torch.equal(nn_b, nn_g)
-    assert torch.allclose(a_b, a_g, rtol=1e-9, atol=1e-9, equal_nan=True) or case == "lattice_ties"   # (rank-deficient fits)
+    monkeypatch.delenv("PM_ICP_MULTI_LAUNCH")               # grid search, whole loop in one cooperative launch
+    a_p, r_p, nn_p = D.icp_affine(D.to_device_points(m), D.to_device_points(f), 3, want_nn=True)
+    assert torch.equal(nn_b, nn_g) and torch.equal(nn_b, nn_p)
+    if case != "lattice_ties":                               # (there the fit is rank deficient: NaN rows)
+        assert torch.allclose(a_b, a_g, rtol=1e-9, atol=1e-9, equal_nan=True)
+        assert torch.allclose(a_b, a_p, rtol=1e-9, atol=1e-9, equal_nan=True)
+        assert torch.allclose(r_b, r_p, rtol=1e-9, atol=1e-12, equal_nan=True)
 
 
 def test_fit_apply_compose(O, torch, golden):
