@@ -467,11 +467,19 @@ pm_icp_persistent_kernel(const double *__restrict__ moving, int n1, const double
             pbuf[(size_t)blockIdx.x * PM_ICP_NSUM + threadIdx.x] = acc;
         }
         grid.sync();
-        if (threadIdx.x < PM_ICP_NSUM) {   // every CTA: the same fixed-order reduction over all CTAs
+        // every CTA: the same fixed-order reduction over all CTAs (5 chunks x 22 terms, then the chunks in order)
+        if (threadIdx.x < 5 * PM_ICP_NSUM) {
+            const int q = threadIdx.x % PM_ICP_NSUM, ch = threadIdx.x / PM_ICP_NSUM;
+            const int per = (nblk + 4) / 5, b0 = ch * per, b1 = min(nblk, b0 + per);
             double acc = 0.0;
-            for (int b = 0; b < nblk; ++b) acc += __ldcg(pbuf + (size_t)b * PM_ICP_NSUM + threadIdx.x);
-            tot[threadIdx.x] = acc;
+#pragma unroll 8
+            for (int b = b0; b < b1; ++b) acc += __ldcg(pbuf + (size_t)b * PM_ICP_NSUM + q);
+            sums[ch][q] = acc;             // (the per-point terms in `sums` were consumed before the grid barrier)
         }
+        __syncthreads();
+        if (threadIdx.x < PM_ICP_NSUM)
+            tot[threadIdx.x] = (((sums[0][threadIdx.x] + sums[1][threadIdx.x]) + sums[2][threadIdx.x]) + sums[3][threadIdx.x]) +
+                               sums[4][threadIdx.x];
         __syncthreads();
         if (threadIdx.x == 0) pm_icp_solve_terms(tot, shift, s_a);
         __syncthreads();
