@@ -1315,8 +1315,12 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
         PM_LAUNCH_CHECK();
         pm_ls_bulk_kernel<<<batch * bulk_ctas, 256, 0, s>>>(B, bulk_ctas);
         PM_LAUNCH_CHECK();
-        PM_CUDA_TRY(cudaFuncSetAttribute(pm_ls_auction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem));
-        pm_ls_auction_kernel<<<batch, 1024, ls_smem, s>>>(B);
+        // the tail kernel is issue-bound: ask for more than half of an SM's shared memory so that two of its
+        // 1024-thread CTAs (a batch of matrices) are never placed on the same SM
+        size_t tail_smem = ls_smem;
+        if (tail_smem < 120 * 1024 && (size_t)smem_optin >= 120 * 1024 + 2048) tail_smem = 120 * 1024;
+        PM_CUDA_TRY(cudaFuncSetAttribute(pm_ls_auction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
+        pm_ls_auction_kernel<<<batch, 1024, tail_smem, s>>>(B);
         PM_LAUNCH_CHECK();
     } else if (max_bid_rounds > 0) {
         int sms = 0, per_sm = 0;
