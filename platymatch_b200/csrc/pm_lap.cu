@@ -1275,7 +1275,7 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
     B.col4row = col4row; B.stats = (long long *)stats; B.total = total;
     // one "round" of the sparse auction = a budget of one bid per row, spread over the 32 warps
     B.max_bids = ((long long)max_bid_rounds * nr + 31) / 32;
-    int bulk_ctas = (nr + 255) / 256;                    // 8 warps per CTA; at most ~2 rows per warp in flight at start
+    int bulk_ctas = (nr + 127) / 128;                    // 8 warps per CTA: ~16 rows per warp at the start
     if (bulk_ctas > 64) bulk_ctas = 64;
     {
         const char *e = getenv("PM_LAP_STOP_LIVE");      // tuning knobs
@@ -1284,7 +1284,7 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
         if (e && atoi(e) > 0) bulk_ctas = atoi(e);
         B.bulk_warps = bulk_ctas * 8;
         e = getenv("PM_LAP_BULK_STOP");
-        B.bulk_stop_live = e ? atoi(e) : 12;
+        B.bulk_stop_live = e ? atoi(e) : (B.bulk_warps / 16 > 8 ? B.bulk_warps / 16 : 8);   // measured optimum at 8k: 24-32 of 512
         e = getenv("PM_LAP_BULK_PATIENCE");
         B.bulk_patience = e ? atoi(e) : 50;
     }
