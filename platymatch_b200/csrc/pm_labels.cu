@@ -112,20 +112,14 @@ __global__ void __launch_bounds__(256) pm_label_accumulate_kernel(const T *__res
                         }
                     }
                     if (__all_sync(0xffffffffu, simple)) {
-                        const unsigned voters = __ballot_sync(0xffffffffu, k > 0);
+                        // one pre-summed item per thread, added with four fire-and-forget reductions (RED.ADD.64):
+                        // cheaper than grouping the 1-3 lanes of a nucleus row first
                         if (k > 0) {
-                            const unsigned peers = __match_any_sync(voters, (unsigned)id1);
-                            const unsigned cnt = __reduce_add_sync(peers, (unsigned)k);
-                            const unsigned sz = __reduce_add_sync(peers, (unsigned)k * pos.z);
-                            const unsigned sy = __reduce_add_sync(peers, (unsigned)k * pos.y);
-                            const unsigned sx = __reduce_add_sync(peers, sxl);
-                            if (lane == __ffs(peers) - 1) {
-                                unsigned long long *a = acc + (size_t)id1 * 4;
-                                atomicAdd(a + 0, (unsigned long long)cnt);
-                                atomicAdd(a + 1, (unsigned long long)sz);
-                                atomicAdd(a + 2, (unsigned long long)sy);
-                                atomicAdd(a + 3, (unsigned long long)sx);
-                            }
+                            unsigned long long *a = acc + (size_t)id1 * 4;
+                            atomicAdd(a + 0, (unsigned long long)k);
+                            atomicAdd(a + 1, (unsigned long long)((unsigned)k * pos.z));
+                            atomicAdd(a + 2, (unsigned long long)((unsigned)k * pos.y));
+                            atomicAdd(a + 3, (unsigned long long)sxl);
                         }
                     } else {
                         PmVox p = pos;
