@@ -28,6 +28,29 @@ def test_oracle_detections_from_labels_known_answers():
     assert det0.shape == (3, 0) and len(sizes0) == 0 and len(ids0) == 0
 
 
+def _rows_golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "rows.npz"))
+
+
+def test_oracle_detections_match_reference_widget():
+    """tests/golden/rows.npz: `self.moving_detections` / `self.fixed_detections` as stored by the reference's own
+    `_click_run` (run headless on a fake widget by oracle/make_golden_rows.py)."""
+    import oracle as O
+    g = _rows_golden()
+    for side in ("moving", "fixed"):
+        det, sizes, ids = O.detections_from_labels(g["label_%s_vol" % side])
+        assert np.array_equal(det, g["label_%s_det" % side])
+
+
+@pytest.mark.gpu
+def test_detections_match_reference_widget():
+    from platymatch_b200.utils.labels import detections_from_labels
+    g = _rows_golden()
+    for side in ("moving", "fixed"):
+        det, sizes, ids = detections_from_labels(g["label_%s_vol" % side])
+        assert np.array_equal(det, g["label_%s_det" % side])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape,n,dtype,sparse", [((64, 96, 128), 60, np.int32, False), ((33, 47, 61), 40, np.uint16, False),
                                                    ((40, 50, 3), 25, np.int32, True), ((128, 128, 128), 400, np.uint16, True),

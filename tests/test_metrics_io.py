@@ -41,6 +41,32 @@ def test_detection_and_transform_files_round_trip(tmp_path):
         load_transform(tmp_path / "bad.txt")
 
 
+def _metric_case(tag):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "rows.npz"))
+    k = lambda name: g["met_%s_%s" % (tag, name)]
+    args = (k("mk"), k("kp_ids"), k("moving"), k("mids"), k("fk"), k("kp_ids"), k("fixed"), k("fids"), k("t1"), k("t2"))
+    return args, float(k("accuracy")), float(k("error"))
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_oracle_metrics_match_reference_widget(tag):
+    """tests/golden/rows.npz: the two numbers the reference's own `EvaluateMetrics._calculate_metrics` wrote into its
+    line edits ('{:.3f}'), run headless on a fake widget by oracle/make_golden_rows.py."""
+    import oracle as O
+    args, acc, err = _metric_case(tag)
+    racc, rerr = O.calculate_metrics(*args)
+    assert float("%.3f" % racc) == acc and float("%.3f" % rerr) == err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_metrics_match_reference_widget(tag):
+    from platymatch_b200.evaluate_metrics import calculate_metrics
+    args, acc, err = _metric_case(tag)
+    gacc, gerr = calculate_metrics(*args)
+    assert float("%.3f" % gacc) == acc and float("%.3f" % gerr) == err
+
+
 @pytest.mark.gpu
 def test_cdist_matches_scipy():
     import torch
