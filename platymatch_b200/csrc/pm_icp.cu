@@ -290,7 +290,6 @@ __device__ __forceinline__ void pm_icp_grid_search(const PmIcpGrid &G, const int
                 for (int y = y0; y <= y1; ++y) {
                     const bool yface = zface || (y == c[1] - r) || (y == c[1] + r);
                     // on a face of the block the whole x-run belongs to ring r, otherwise only its two ends
-                    const int xa = yface ? x0 : ((c[2] - r >= 0) ? c[2] - r : x1 + 1);
                     const int row = (z * G.g[1] + y) * G.g[2];
                     auto scan_cells = [&](int xs, int xe) {     // contiguous cells -> contiguous sorted points
                         if (xs > xe) return;
@@ -314,7 +313,6 @@ __device__ __forceinline__ void pm_icp_grid_search(const PmIcpGrid &G, const int
                         if (c[2] - r >= 0) scan_cells(c[2] - r, c[2] - r);
                         if (r > 0 && c[2] + r <= G.g[2] - 1) scan_cells(c[2] + r, c[2] + r);
                     }
-                    (void)xa;
                 }
             }
             if (NSUB > 1) {     // merge the lanes of this query: minimum of (distance, index)

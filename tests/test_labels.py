@@ -28,6 +28,13 @@ def test_oracle_detections_from_labels_known_answers():
     assert det0.shape == (3, 0) and len(sizes0) == 0 and len(ids0) == 0
 
 
+def test_ransac_error_from_sizes_host_logic():
+    """reference _dock_widget.py:613-618 (no GPU involved)."""
+    from platymatch_b200.utils.labels import ransac_error_from_sizes
+    assert ransac_error_from_sizes(None, [1.0]) == 16 and ransac_error_from_sizes([], []) == 16
+    assert ransac_error_from_sizes([8.0, 8.0], [27.0, 27.0, 27.0]) == pytest.approx(2.5)
+
+
 def _rows_golden():
     return np.load(os.path.join(ROOT, "tests", "golden", "rows.npz"))
 
