@@ -107,7 +107,8 @@ struct PmLapBatch {   // passed by value to kernels
     char *ws; PmLapLayout L;
     int32_t *col4row; long long *stats; double *total;
     int32_t *progress;   // [2] assignments made in the current / previous bidding round
-    long long max_bids;  // sparse auction: bid budget per warp
+    long long max_bids;       // sparse auction: bid budget per warp of the bulk kernel
+    long long max_bids_tail;  // ... and of the tail kernel
     int stop_live;       // sparse auction: stop carrying displaced rows once this few warps are still bidding
     int bulk_stop_live;  // bulk kernel: stop once this few warps (of bulk_warps) are still bidding
     int bulk_warps;
@@ -673,7 +674,7 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
     long long bids = 0, refreshes = 0, retries = 0, parked = 0, refresh_cycles = 0;
     const long long t_begin = clock64();
     int carry = -1;          // displaced owner this warp continues with (only when nothing is queued)
-    while (bids < B.max_bids) {
+    while (bids < B.max_bids_tail) {
         // ---- next row: fresh rows first, then displaced owners in FIFO order
         int row = carry;
         carry = -1;
@@ -1275,6 +1276,7 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
     B.col4row = col4row; B.stats = (long long *)stats; B.total = total;
     // one "round" of the sparse auction = a budget of one bid per row, spread over the 32 warps
     B.max_bids = ((long long)max_bid_rounds * nr + 31) / 32;
+    B.max_bids_tail = B.max_bids;
     int bulk_ctas = (nr + 127) / 128;                    // 8 warps per CTA: ~16 rows per warp at the start
     if (bulk_ctas > 64) bulk_ctas = 64;
     {
@@ -1285,6 +1287,13 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
         B.bulk_warps = bulk_ctas * 8;
         e = getenv("PM_LAP_BULK_STOP");
         B.bulk_stop_live = e ? atoi(e) : (B.bulk_warps / 16 > 8 ? B.bulk_warps / 16 : 8);   // measured optimum at 8k: 24-32 of 512
+        // Safety net.  A typical 8k matrix needs 17-36 bids per row in total.  Problems without slack columns
+        // (nr == nc) need an order of magnitude more, almost all of them in long sequential price wars that the
+        // augmenting-path phase settles much faster: cap the auction at ~64 bids per row (bulk) + ~16 (tail),
+        // with a 4x allowance for imbalance between warps.
+        const long long cap_bulk = 4ll * 64 * nr / B.bulk_warps, cap_tail = 4ll * 16 * nr / 32;
+        if (B.max_bids > (cap_bulk > 1024 ? cap_bulk : 1024)) B.max_bids = cap_bulk > 1024 ? cap_bulk : 1024;
+        if (B.max_bids_tail > (cap_tail > 1024 ? cap_tail : 1024)) B.max_bids_tail = cap_tail > 1024 ? cap_tail : 1024;
         e = getenv("PM_LAP_BULK_PATIENCE");
         B.bulk_patience = e ? atoi(e) : 50;
     }

@@ -57,8 +57,9 @@ def make_keypoints(pair, n_keypoints=10, seed=0, jitter=1.0):
     return mk, fk
 
 
-def make_specimens(n_specimens=12, n_nuclei=8000, jitter=2.0, dropout=0.10, seed=0):
-    """Batched all-pairs config: specimens are random-affine, jittered, thinned views of one atlas."""
+def make_specimens(n_specimens=12, n_nuclei=8000, jitter=2.0, dropout=0.10, seed=0, vary=0.05):
+    """Batched all-pairs config: specimens are random-affine, jittered, thinned views of one atlas with ~n_nuclei
+    nuclei each (detections of real specimens never have exactly equal counts: n_nuclei * (1 - U(0, vary)))."""
     rng = np.random.default_rng(seed)
     atlas = make_fixed_cloud(int(round(n_nuclei / (1.0 - dropout))), rng)
     out = []
@@ -66,7 +67,8 @@ def make_specimens(n_specimens=12, n_nuclei=8000, jitter=2.0, dropout=0.10, seed
         r = np.random.default_rng(1000 + s)
         a = random_affine(r)
         pts = a[:3, :3] @ atlas + a[:3, 3:4] + r.normal(0.0, jitter, size=atlas.shape)
-        keep = r.permutation(atlas.shape[1])[:n_nuclei]
+        n_s = n_nuclei if not vary else int(round(n_nuclei * (1.0 - vary * r.random())))
+        keep = r.permutation(atlas.shape[1])[:n_s]
         out.append({"points": np.ascontiguousarray(pts[:, keep]), "A": a, "atlas_index": keep})
     return out
 
