@@ -462,9 +462,10 @@ def run_b200(args):
                       "refresh_cycles": [s[9] for s in lap_stats], "auction_cycles": [s[10] for s in lap_stats],
                       "bulk_bids": [s[11] for s in lap_stats], "sap_dense_relax": [s[12] for s in lap_stats]},
     }
-    if not args.no_rows:
+    # the CPU baseline and the secondary rows are single-GPU measurements (rank 0 at N = 1 only)
+    if not args.no_rows and world == 1:
         line["rows"] = {"label_centroids": bench_label_row(torch, D, hbm_peak, not args.no_cpu_baseline)}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         cb = cpu_sample(pairs[0], args.trials, ICP_ITERS)
         line["cpu_baseline"] = {"value": 1.0 / cb["seconds_per_registration"], "unit": "registrations/s",
                                 "cores": cb["cores"], "kind": "port", "sample": cb["sample"], "stages_s": cb["stages"],
