@@ -25,6 +25,19 @@ def test_header_symbols_exported_and_bound():
     assert set(_lib.SIGNATURES) == set(names)
 
 
+def test_ctypes_signatures_match_header_arity():
+    """Every ctypes signature has as many arguments as the header's prototype (ABI drift shows up here, on the CPU)."""
+    from platymatch_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "platymatch_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = dict(re.findall(r"\b(pm_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S))
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, params in protos.items():
+        params = " ".join(params.split())
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))
+
+
 def test_version_and_sizes_without_gpu():
     from platymatch_b200 import _lib
     lib = _lib.load()
