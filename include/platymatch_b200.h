@@ -38,6 +38,9 @@ extern "C" {
 #define PM_ERR_UNSUPPORTED (-5)
 
 #define PM_NBINS 360          /* 5 r x 6 theta x 12 phi  (shape_context.py:10) */
+/* the widget's "Transform" choice (_dock_widget.py:627; shape_context.py:126-129, perform_icp.py:17-20) */
+#define PM_TRANSFORM_AFFINE 0
+#define PM_TRANSFORM_SIMILAR 1
 #define PM_STATS_DOUBLES 16   /* layout of the cloud-stats block, see pm_cloud_stats */
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -178,6 +181,13 @@ int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ldc, int max_
  *   inliers_per_trial  [trials] int32 out, may be NULL.
  * workspace: pm_ransac_workspace_bytes(trials). */
 size_t pm_ransac_workspace_bytes(int trials);
+/* do_ransac with its `transform` argument: PM_TRANSFORM_AFFINE fits get_affine_transform on the sampled pairs
+ * (degenerate samples: pinv's minimum-norm answer), PM_TRANSFORM_SIMILAR fits get_similar_transform
+ * (find_transform.py:21-99, Horn's closed form with the eigenvector of the largest eigenvalue). */
+int pm_ransac(const double *moving, const double *fixed, int k, const int32_t *sample_idx, int trials, int min_samples,
+              double error, unsigned long long seed, int transform, double *best_A, int32_t *best_inliers,
+              int32_t *best_trial, int32_t *inliers_per_trial, void *workspace, size_t workspace_bytes, void *stream);
+/* = pm_ransac(..., PM_TRANSFORM_AFFINE, ...) */
 int pm_ransac_affine(const double *moving, const double *fixed, int k, const int32_t *sample_idx, int trials,
                      int min_samples, double error, unsigned long long seed, double *best_A,
                      int32_t *best_inliers, int32_t *best_trial, int32_t *inliers_per_trial, void *workspace,
@@ -193,12 +203,22 @@ int pm_ransac_affine(const double *moving, const double *fixed, int k, const int
  * workspace: pm_icp_workspace_bytes(n1). */
 size_t pm_icp_workspace_bytes(int n1);            /* brute-force nearest neighbour only */
 size_t pm_icp_workspace_bytes2(int n1, int n2);  /* + the uniform grid over the fixed cloud (exact, ~50x fewer candidates) */
+/* perform_icp with its `transform` argument (re-fit = get_affine_transform or get_similar_transform, :17-20) */
+int pm_icp(const double *moving, int n1, const double *fixed, int n2, int iterations, int transform, double *A_icp,
+           double *residuals, int32_t *nn_out, void *workspace, size_t workspace_bytes, void *stream);
+/* = pm_icp(..., PM_TRANSFORM_AFFINE, ...) */
 int pm_icp_affine(const double *moving, int n1, const double *fixed, int n2, int iterations, double *A_icp,
                   double *residuals, int32_t *nn_out, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- small ops -------------------------------------------------------------------------------------
- * get_affine_transform (find_transform.py:4-17) for K >= 4 pairs, normal equations in float64. */
+ * get_affine_transform (find_transform.py:4-17) = fixed_h @ pinv(moving_h) for K >= 1 pairs: float64 normal
+ * equations; rank-deficient point sets (coplanar keypoints, K < 4) get pinv's minimum-norm solution. */
 int pm_fit_affine(const double *moving, const double *fixed, int k, double *A, void *stream);
+/* get_similar_transform (find_transform.py:21-99): scale * rotation + translation by Horn's closed form. */
+int pm_fit_similar(const double *moving, const double *fixed, int k, double *A, void *stream);
+/* np.argmax(inliers) of the pipeline (_dock_widget.py:683-703), on the device: best[0] = first maximum of
+ * inliers[n_hyp], A_best[16] = A_all[best] ([n_hyp][16]). */
+int pm_select_best(const int32_t *inliers, const double *A_all, int n_hyp, int32_t *best, double *A_best, void *stream);
 /* apply_affine_transform (apply_transform.py:3-17): out[i] = (A [p_i;1])[:3];  in-place allowed. */
 int pm_apply_affine(const double *pts, int n, const double *A, double *out, void *stream);
 /* out[i] = pts[index[i]] (the reordering moving[:, row_ind] / fixed[:, col_ind], _dock_widget.py:622-623) */

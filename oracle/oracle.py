@@ -237,6 +237,50 @@ def get_affine_transform(moving, fixed, with_ones=False):
     return np.matmul(fixed, np.linalg.pinv(moving))
 
 
+def get_similar_transform(moving, fixed, as_shipped=False):
+    """find_transform.py:21-99, line by line.  as_shipped=True keeps `q = D[0]` (:66, the first ROW of numpy's
+    eigenvector matrix: LAPACK-dependent signs, not a rotation); the default is Horn's method as published
+    (`q = D[:, 0]`, the eigenvector of the largest eigenvalue), which is what the CUDA path implements."""
+    moving = np.asarray(moving, dtype=np.float64)
+    fixed = np.asarray(fixed, dtype=np.float64)
+    com_target = np.mean(fixed, 1, keepdims=True)                       # :27
+    com_source = np.mean(moving, 1, keepdims=True)                      # :28
+    Yprime = fixed[:3, :] - com_target[:3, :]                           # :31
+    Pprime = moving[:3, :] - com_source[:3, :]                          # :32
+    Px, Py, Pz = Pprime[0, :], Pprime[1, :], Pprime[2, :]
+    Yx, Yy, Yz = Yprime[0, :], Yprime[1, :], Yprime[2, :]
+    Sxx, Sxy, Sxz = np.sum(Yx * Px), np.sum(Px * Yy), np.sum(Px * Yz)   # :44-46
+    Syx, Syy, Syz = np.sum(Py * Yx), np.sum(Py * Yy), np.sum(Py * Yz)   # :48-50
+    Szx, Szy, Szz = np.sum(Pz * Yx), np.sum(Pz * Yy), np.sum(Pz * Yz)   # :52-54
+    Nmatrix = [[Sxx + Syy + Szz, Syz - Szy, -Sxz + Szx, Sxy - Syx],     # :56-59
+               [-Szy + Syz, Sxx - Szz - Syy, Sxy + Syx, Sxz + Szx],
+               [Szx - Sxz, Syx + Sxy, Syy - Szz - Sxx, Syz + Szy],
+               [-Syx + Sxy, Szx + Sxz, Szy + Syz, Szz - Syy - Sxx]]
+    V, D = np.linalg.eig(Nmatrix)                                       # :61
+    idx = V.argsort()[::-1]                                             # :63
+    D = D[:, idx]                                                       # :65
+    q = D[0] if as_shipped else D[:, 0]                                 # :66
+    q0, q1, q2, q3 = q[0], q[1], q[2], q[3]
+    Qbar = [[q0, -q1, -q2, -q3], [q1, q0, q3, -q2], [q2, -q3, q0, q1], [q3, q2, -q1, q0]]     # :72-75
+    Q = [[q0, -q1, -q2, -q3], [q1, q0, -q3, q2], [q2, q3, q0, -q1], [q3, -q2, q1, q0]]        # :77-80
+    R = np.matmul(np.transpose(Qbar), Q)[1:, 1:]                        # :82-83
+    s = np.sqrt(np.sum(Yprime * Yprime) / np.sum(Pprime * Pprime))      # :86-94
+    t = com_target[:3, :] - s * np.matmul(R, com_source[:3, :])         # :95
+    A = np.zeros((4, 4))
+    A[:3, :3] = s * R
+    A[:3, 3:4] = t
+    A[3, 3] = 1
+    return A
+
+
+def fit_transform(moving, fixed, transform="Affine", as_shipped=False):
+    if transform == "Affine":
+        return get_affine_transform(moving, fixed)
+    if transform == "Similar":
+        return get_similar_transform(moving, fixed, as_shipped)
+    raise ValueError(transform)
+
+
 def apply_affine_transform(moving, affine_transform_matrix):
     """apply_transform.py:3-17."""
     moving = np.asarray(moving, dtype=np.float64)[:3, :]
@@ -253,9 +297,8 @@ def ransac_sample_indices(k, min_samples, trials, seed):
 
 
 def do_ransac(moving_all, fixed_all, min_samples=4, trials=500, error=5, transform="Affine", sample_indices=None,
-              seed=None, return_all=False):
+              seed=None, return_all=False, as_shipped=False):
     """shape_context.py:103-139 with the sample-index stream made explicit (first strictly-better wins)."""
-    assert transform == "Affine"
     moving_all = np.asarray(moving_all, dtype=np.float64)[:3, :]
     fixed_all = np.asarray(fixed_all, dtype=np.float64)[:3, :]
     k = fixed_all.shape[1]
@@ -265,7 +308,7 @@ def do_ransac(moving_all, fixed_all, min_samples=4, trials=500, error=5, transfo
     mats = np.empty((trials, 4, 4))
     for t in range(trials):
         idx = sample_indices[t]
-        mats[t] = get_affine_transform(moving_all[:, idx], fixed_all[:, idx])
+        mats[t] = fit_transform(moving_all[:, idx], fixed_all[:, idx], transform, as_shipped)
     m = np.ascontiguousarray(moving_all.T)
     f = np.ascontiguousarray(fixed_all.T)
     inl = np.zeros(trials, dtype=np.int32)
@@ -290,16 +333,15 @@ def nearest(moving, fixed):
     return nn, dist
 
 
-def perform_icp(moving, fixed, icp_iterations=50, transform="Affine", return_residuals=False):
+def perform_icp(moving, fixed, icp_iterations=50, transform="Affine", return_residuals=False, as_shipped=False):
     """perform_icp.py:7-26."""
-    assert transform == "Affine"
     moving = np.asarray(moving, dtype=np.float64)[:3, :]
     fixed = np.asarray(fixed, dtype=np.float64)[:3, :]
     a_icp = np.identity(4)
     residuals = []
     for _ in range(icp_iterations):
         i2, _d = nearest(moving, fixed)
-        a_est = get_affine_transform(moving, fixed[:, i2])
+        a_est = fit_transform(moving, fixed[:, i2], transform, as_shipped)
         moving = apply_affine_transform(moving, a_est)
         residuals.append(get_error(moving, fixed[:, i2]))
         a_icp = np.matmul(a_est, a_icp)
@@ -313,7 +355,8 @@ HYPOTHESES = [(1, 1), (1, 2), (1, 3), (1, 4), (2, 1), (2, 2), (2, 3), (2, 4)]  #
 
 
 def estimate_transform_unsupervised(moving, fixed, ransac_samples=4, ransac_trials=8000, ransac_error=16,
-                                    icp_iterations=50, seed=0, hypotheses=None, sample_indices=None):
+                                    icp_iterations=50, seed=0, hypotheses=None, sample_indices=None,
+                                    transform="Affine"):
     moving = np.asarray(moving, dtype=np.float64)
     fixed = np.asarray(fixed, dtype=np.float64)
     mc, fc = get_centroid(moving, False), get_centroid(fixed, False)
@@ -330,22 +373,26 @@ def estimate_transform_unsupervised(moving, fixed, ransac_samples=4, ransac_tria
             idx = sample_indices[q]
         else:
             idx = np.stack([rs.choice(len(r), ransac_samples, replace=False) for _ in range(ransac_trials)])
-        A, inl = do_ransac(moving[:, r], fixed[:, c], ransac_samples, ransac_trials, ransac_error, sample_indices=idx)
+        A, inl = do_ransac(moving[:, r], fixed[:, c], ransac_samples, ransac_trials, ransac_error, transform,
+                           sample_indices=idx)
         res["inliers"].append(inl)
         res["ransac_A"].append(A)
         res["assignments"].append((r, c))
         res["lap_cost"].append(float(U[r, c].sum()))
     best = int(np.argmax(res["inliers"]))
     a_sc = res["ransac_A"][best]
-    a_icp, resid = perform_icp(apply_affine_transform(moving, a_sc), fixed, icp_iterations, return_residuals=True)
+    a_icp, resid = perform_icp(apply_affine_transform(moving, a_sc), fixed, icp_iterations, transform,
+                               return_residuals=True)
     res.update(best=best, transform_sc=a_sc, transform_icp=a_icp, transform=a_icp @ a_sc, icp_residuals=resid)
     return res
 
 
-def estimate_transform_supervised(moving, fixed, moving_keypoints, fixed_keypoints, icp_iterations=50):
-    """_dock_widget.py:707-717: LS affine on the keypoints, then ICP."""
-    a_sc = get_affine_transform(moving_keypoints, fixed_keypoints)
-    a_icp, resid = perform_icp(apply_affine_transform(moving, a_sc), fixed, icp_iterations, return_residuals=True)
+def estimate_transform_supervised(moving, fixed, moving_keypoints, fixed_keypoints, icp_iterations=50,
+                                  transform="Affine"):
+    """_dock_widget.py:707-717: LS affine (or similarity, :710-711) on the keypoints, then ICP."""
+    a_sc = fit_transform(moving_keypoints, fixed_keypoints, transform)
+    a_icp, resid = perform_icp(apply_affine_transform(moving, a_sc), fixed, icp_iterations, transform,
+                               return_residuals=True)
     return dict(transform_sc=a_sc, transform_icp=a_icp, transform=a_icp @ a_sc, icp_residuals=resid)
 
 

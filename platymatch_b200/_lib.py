@@ -13,6 +13,7 @@ NBINS = 360
 LAP_STATS = 16
 CHI2_EPS = 2.0 ** -60
 CHI2_TILE = 128
+TRANSFORMS = {"Affine": 0, "Similar": 1}      # PM_TRANSFORM_* (the widget's strings, _dock_widget.py:627)
 
 _vp, _i, _d, _sz, _u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t, ctypes.c_ulonglong
 
@@ -39,11 +40,15 @@ SIGNATURES = {
     "pm_lap_workspace_bytes": (_sz, [_i, _i, _i]),
     "pm_lap_solve": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pm_ransac_workspace_bytes": (_sz, [_i]),
+    "pm_ransac": (_i, [_vp, _vp, _i, _vp, _i, _i, _d, _u64, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pm_ransac_affine": (_i, [_vp, _vp, _i, _vp, _i, _i, _d, _u64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pm_icp_workspace_bytes": (_sz, [_i]),
     "pm_icp_workspace_bytes2": (_sz, [_i, _i]),
+    "pm_icp": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pm_icp_affine": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pm_fit_affine": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "pm_fit_similar": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "pm_select_best": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "pm_apply_affine": (_i, [_vp, _i, _vp, _vp, _vp]),
     "pm_gather_points": (_i, [_vp, _vp, _i, _vp, _vp]),
     "pm_compose": (_i, [_vp, _vp, _vp, _vp]),

@@ -175,8 +175,9 @@ extern "C" int pm_mean_distance(const double *pts, int n, double *out_mean, void
 }
 
 // ------------------------------------------------------------------------------------ small ops
-// Least-squares affine over K pairs: A = F_h M_h^T (M_h M_h^T)^-1 (== fixed_h @ pinv(moving_h) for
-// full-rank M_h).  Moving coordinates are shifted by moving[0] before forming the normal equations
+// Least-squares affine over K pairs: A = F_h M_h^T (M_h M_h^T)^+ == fixed_h @ pinv(moving_h), also for
+// rank-deficient (coplanar, collinear, K < 4) point sets, where it is pinv's minimum-norm solution
+// (pm_linalg.cuh).  Moving coordinates are shifted by moving[0] before forming the normal equations
 // (block conditioning), and the shift is folded back into the translation column.
 __global__ void __launch_bounds__(256) pm_fit_affine_kernel(const double *__restrict__ moving,
                                                             const double *__restrict__ fixed, int k,
@@ -206,23 +207,79 @@ __global__ void __launch_bounds__(256) pm_fit_affine_kernel(const double *__rest
     int q = 0;
     for (int a = 0; a < 4; ++a)
         for (int b = a; b < 4; ++b) { M[a * 4 + b] = mm[q]; M[b * 4 + a] = mm[q]; ++q; }
-    double X[12];
-    const bool ok = pm_solve_right_4x4(M, fm, 3, X, 1e-14);
-    for (int r = 0; r < 3; ++r) {
-        if (ok) {
-            A[r * 4 + 0] = X[r * 4 + 0]; A[r * 4 + 1] = X[r * 4 + 1]; A[r * 4 + 2] = X[r * 4 + 2];
-            A[r * 4 + 3] = X[r * 4 + 3] - (X[r * 4 + 0] * c0 + X[r * 4 + 1] * c1 + X[r * 4 + 2] * c2);
-        } else {
-            for (int c = 0; c < 4; ++c) A[r * 4 + c] = nan("");
-        }
-    }
-    A[12] = 0.0; A[13] = 0.0; A[14] = 0.0; A[15] = 1.0;
+    const double shift[3] = {c0, c1, c2};
+    pm_affine_from_normal_eq(M, fm, shift, 1e-14, A);     // rank-deficient point sets: pinv's minimum-norm answer
 }
 
 extern "C" int pm_fit_affine(const double *moving, const double *fixed, int k, double *A, void *stream) {
     PM_REQUIRE(moving && fixed && A, "null pointer");
-    PM_REQUIRE(k >= 4, "need at least 4 pairs");
+    PM_REQUIRE(k >= 1, "need at least 1 pair");
     pm_fit_affine_kernel<<<1, 256, 0, pm_stream(stream)>>>(moving, fixed, k, A);
+    PM_LAUNCH_CHECK();
+    return PM_OK;
+}
+
+// get_similar_transform (find_transform.py:21-99): Horn's closed form over K pairs, two passes like the reference
+// (centroids :27-28, then centred moments :31-54,:88-94).  One CTA, fixed-order reductions.
+__global__ void __launch_bounds__(256) pm_fit_similar_kernel(const double *__restrict__ moving,
+                                                             const double *__restrict__ fixed, int k,
+                                                             double *__restrict__ A) {
+    __shared__ double red[32];
+    double c[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < k; i += blockDim.x)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { c[a] += moving[3 * i + a]; c[3 + a] += fixed[3 * i + a]; }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) c[q] = pm_block_sum(c[q], red) / (double)k;
+    double v[11] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const double p[3] = {moving[3 * i] - c[0], moving[3 * i + 1] - c[1], moving[3 * i + 2] - c[2]};
+        const double y[3] = {fixed[3 * i] - c[3], fixed[3 * i + 1] - c[4], fixed[3 * i + 2] - c[5]};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int b = 0; b < 3; ++b) v[a * 3 + b] += p[a] * y[b];
+            v[9] += p[a] * p[a];
+            v[10] += y[a] * y[a];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 11; ++q) v[q] = pm_block_sum(v[q], red);
+    if (threadIdx.x != 0) return;
+    double out[16];
+    pm_similar_from_moments(c, c + 3, v, v[9], v[10], out);
+    for (int e = 0; e < 16; ++e) A[e] = out[e];
+}
+
+extern "C" int pm_fit_similar(const double *moving, const double *fixed, int k, double *A, void *stream) {
+    PM_REQUIRE(moving && fixed && A, "null pointer");
+    PM_REQUIRE(k >= 1, "need at least 1 pair");
+    pm_fit_similar_kernel<<<1, 256, 0, pm_stream(stream)>>>(moving, fixed, k, A);
+    PM_LAUNCH_CHECK();
+    return PM_OK;
+}
+
+// np.argmax over the hypotheses' inlier counts (first maximum, _dock_widget.py:683-703) on the device, so that
+// the registration never returns to the host between RANSAC and ICP: best index + that hypothesis' 4x4.
+__global__ void pm_select_best_kernel(const int32_t *__restrict__ inliers, const double *__restrict__ A_all, int n_hyp,
+                                      int32_t *__restrict__ best, double *__restrict__ A_best) {
+    __shared__ int s_best;
+    if (threadIdx.x == 0) {
+        int b = 0;
+        for (int q = 1; q < n_hyp; ++q)
+            if (inliers[q] > inliers[b]) b = q;
+        s_best = b;
+        best[0] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) A_best[threadIdx.x] = A_all[(size_t)s_best * 16 + threadIdx.x];
+}
+
+extern "C" int pm_select_best(const int32_t *inliers, const double *A_all, int n_hyp, int32_t *best, double *A_best,
+                              void *stream) {
+    PM_REQUIRE(inliers && A_all && best && A_best, "null pointer");
+    PM_REQUIRE(n_hyp >= 1, "need at least one hypothesis");
+    pm_select_best_kernel<<<1, 32, 0, pm_stream(stream)>>>(inliers, A_all, n_hyp, best, A_best);
     PM_LAUNCH_CHECK();
     return PM_OK;
 }

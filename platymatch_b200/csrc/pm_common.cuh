@@ -57,39 +57,4 @@ __device__ __forceinline__ double pm_block_sum(double v, double *smem32) {
     return r;
 }
 
-// 4x4 float64 linear solve helpers (device): solve X * M = R for X (rows of R independent), i.e.
-// X = R * inv(M), by Gauss-Jordan with partial pivoting on M^T.  Returns false if singular.
-__device__ inline bool pm_solve_right_4x4(const double M[16], const double *R, int nrows, double *X,
-                                          double rel_tol) {
-    // Solve M^T x_r^T = R_r^T for every row r.  Augmented matrix [M^T | R^T].
-    double a[4][4 + 4];
-    double scale = 0.0;
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) {
-            a[i][j] = M[j * 4 + i];
-            scale = fmax(scale, fabs(a[i][j]));
-        }
-    for (int i = 0; i < 4; ++i)
-        for (int r = 0; r < nrows; ++r) a[i][4 + r] = R[r * 4 + i];
-    if (!(scale > 0.0) || !isfinite(scale)) return false;
-    for (int c = 0; c < 4; ++c) {
-        int piv = c;
-        double best = fabs(a[c][c]);
-        for (int i = c + 1; i < 4; ++i)
-            if (fabs(a[i][c]) > best) { best = fabs(a[i][c]); piv = i; }
-        if (!(best > rel_tol * scale)) return false;
-        if (piv != c)
-            for (int j = 0; j < 4 + nrows; ++j) { double t = a[c][j]; a[c][j] = a[piv][j]; a[piv][j] = t; }
-        const double inv = 1.0 / a[c][c];
-        for (int j = c; j < 4 + nrows; ++j) a[c][j] *= inv;
-        for (int i = 0; i < 4; ++i) {
-            if (i == c) continue;
-            const double f = a[i][c];
-            if (f != 0.0)
-                for (int j = c; j < 4 + nrows; ++j) a[i][j] -= f * a[c][j];
-        }
-    }
-    for (int r = 0; r < nrows; ++r)
-        for (int i = 0; i < 4; ++i) X[r * 4 + i] = a[i][4 + r];
-    return true;
-}
+#include "pm_linalg.cuh"   // pm_solve_right_4x4, pm_jacobi_sym4, pm_affine_from_normal_eq, pm_similar_from_moments

@@ -1,4 +1,4 @@
-// pm_icp.cu — K6: ICP refinement with affine re-fit.
+// pm_icp.cu — K6: ICP refinement with affine (or similarity, perform_icp.py:19-20) re-fit.
 //
 // Reference: platymatch/estimate_transform/perform_icp.py:7-26.  Per iteration:
 //   cost = distance_matrix(moving^T, fixed^T); i2 = argmin(cost, 1)          (:15-16, first min wins)
@@ -23,11 +23,62 @@ namespace cg = cooperative_groups;
 #define PM_ICP_TILE 512    // fixed points staged per tile
 #define PM_ICP_NSUM 22     // 10 (M M^T upper) + 12 (F M^T)
 
+// normal-equation terms of one correspondence: 10 (M M^T upper) + 12 (F M^T).
+// transform = PM_TRANSFORM_SIMILAR (perform_icp.py:19-20): Horn's fit needs the same sums (n, sum m, sum f,
+// sum f m^T, sum |m|^2 = trace of the M M^T block) plus sum |f|^2, which takes the slot of the unused m_x m_y term
+// (fixed coordinates shifted by fixed[0] for conditioning).
+__device__ __forceinline__ void pm_icp_terms(double mx, double my, double mz, const double *__restrict__ shift,
+                                             const double *__restrict__ fixed, int bj, int transform,
+                                             double v[PM_ICP_NSUM]) {
+    const double m[4] = {mx - shift[0], my - shift[1], mz - shift[2], 1.0};
+    const double f[3] = {fixed[3 * (size_t)bj], fixed[3 * (size_t)bj + 1], fixed[3 * (size_t)bj + 2]};
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = a; b < 4; ++b) v[q++] = m[a] * m[b];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) v[q++] = f[a] * m[b];
+    if (transform == PM_TRANSFORM_SIMILAR) {
+        const double g0 = f[0] - fixed[0], g1 = f[1] - fixed[1], g2 = f[2] - fixed[2];
+        v[1] = g0 * g0 + g1 * g1 + g2 * g2;
+    }
+}
+
+// A_est (4x4, row-major) from the 22 summed terms: fixed_h @ pinv(moving_h) (rank-deficient clouds included), or
+// Horn's similarity from the same sums
+__device__ __noinline__ void pm_icp_solve_terms(const double *tot, const double *__restrict__ shift,
+                                          const double *__restrict__ fixed, int transform, double A[16]) {
+    if (transform == PM_TRANSFORM_SIMILAR) {
+        // slots: (0,0)=0 (0,1)=1* (0,2)=2 (0,3)=3 (1,1)=4 (1,2)=5 (1,3)=6 (2,2)=7 (2,3)=8 (3,3)=9;  F M^T at 10 + 4 a + b
+        const double n = tot[9];
+        const double sm[3] = {tot[3], tot[6], tot[8]}, sf[3] = {tot[13], tot[17], tot[21]};
+        double cp[3], cy[3], S[9];
+        for (int a = 0; a < 3; ++a) { cp[a] = shift[a] + sm[a] / n; cy[a] = sf[a] / n; }
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) S[a * 3 + b] = tot[10 + b * 4 + a] - sm[a] * sf[b] / n;
+        const double spp = (tot[0] + tot[4] + tot[7]) - (sm[0] * sm[0] + sm[1] * sm[1] + sm[2] * sm[2]) / n;
+        const double g[3] = {cy[0] - fixed[0], cy[1] - fixed[1], cy[2] - fixed[2]};
+        const double syy = tot[1] - n * (g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+        pm_similar_from_moments(cp, cy, S, spp, syy, A);
+        return;
+    }
+    double M[16];
+    int k = 0;
+    for (int a = 0; a < 4; ++a)
+        for (int b = a; b < 4; ++b) { M[a * 4 + b] = tot[k]; M[b * 4 + a] = tot[k]; ++k; }
+    const double sh[3] = {shift[0], shift[1], shift[2]};
+    pm_affine_from_normal_eq(M, tot + 10, sh, 1e-14, A);   // rank-deficient clouds: pinv's minimum-norm answer
+}
+
 // cur: current moving positions [n1][3]; shift: 3 doubles subtracted from moving coordinates when
 // forming the normal equations (conditioning); partial: [gridDim.x][PM_ICP_NSUM].
 __global__ void __launch_bounds__(PM_ICP_PTS * PM_ICP_SLICES)
 pm_icp_nn_kernel(const double *__restrict__ cur, int n1, const double *__restrict__ fixed, int n2,
-                 const double *__restrict__ shift, int32_t *__restrict__ nn, double *__restrict__ partial) {
+                 const double *__restrict__ shift, int transform, int32_t *__restrict__ nn,
+                 double *__restrict__ partial) {
     __shared__ __align__(16) double tile[2][PM_ICP_TILE * 3];      // double-buffered with cp.async
     __shared__ double best_d[PM_ICP_SLICES][PM_ICP_PTS];
     __shared__ int best_j[PM_ICP_SLICES][PM_ICP_PTS];
@@ -104,17 +155,7 @@ pm_icp_nn_kernel(const double *__restrict__ cur, int n1, const double *__restric
         if (live) {
             if (bj == 0x7fffffff) bj = 0;        // no finite distance at all: np.argmin of an all-NaN row
             nn[i] = bj;
-            const double m[4] = {mx - shift[0], my - shift[1], mz - shift[2], 1.0};
-            const double f[3] = {fixed[3 * (size_t)bj], fixed[3 * (size_t)bj + 1], fixed[3 * (size_t)bj + 2]};
-            int q = 0;
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = a; b < 4; ++b) v[q++] = m[a] * m[b];
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) v[q++] = f[a] * m[b];
+            pm_icp_terms(mx, my, mz, shift, fixed, bj, transform, v);
         }
 #pragma unroll
         for (int q = 0; q < PM_ICP_NSUM; ++q) sums[p][q] = v[q];
@@ -336,45 +377,12 @@ __device__ __forceinline__ void pm_icp_grid_search(const PmIcpGrid &G, const int
         }
 }
 
-// normal-equation terms of one correspondence: 10 (M M^T upper) + 12 (F M^T)
-__device__ __forceinline__ void pm_icp_terms(double mx, double my, double mz, const double *__restrict__ shift,
-                                             const double *__restrict__ fixed, int bj, double v[PM_ICP_NSUM]) {
-    const double m[4] = {mx - shift[0], my - shift[1], mz - shift[2], 1.0};
-    const double f[3] = {fixed[3 * (size_t)bj], fixed[3 * (size_t)bj + 1], fixed[3 * (size_t)bj + 2]};
-    int q = 0;
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = a; b < 4; ++b) v[q++] = m[a] * m[b];
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) v[q++] = f[a] * m[b];
-}
-
-// A_est (4x4, row-major) from the 22 summed terms; NaN rows when the moving points are rank deficient
-__device__ inline void pm_icp_solve_terms(const double *tot, const double *__restrict__ shift, double A[16]) {
-    double M[16], X[12];
-    int k = 0;
-    for (int a = 0; a < 4; ++a)
-        for (int b = a; b < 4; ++b) { M[a * 4 + b] = tot[k]; M[b * 4 + a] = tot[k]; ++k; }
-    const bool ok = pm_solve_right_4x4(M, tot + 10, 3, X, 1e-14);
-    for (int r = 0; r < 3; ++r) {
-        if (ok) {
-            A[r * 4 + 0] = X[r * 4 + 0]; A[r * 4 + 1] = X[r * 4 + 1]; A[r * 4 + 2] = X[r * 4 + 2];
-            A[r * 4 + 3] = X[r * 4 + 3] - (X[r * 4 + 0] * shift[0] + X[r * 4 + 1] * shift[1] + X[r * 4 + 2] * shift[2]);
-        } else {
-            for (int c = 0; c < 4; ++c) A[r * 4 + c] = nan("");
-        }
-    }
-    A[12] = 0.0; A[13] = 0.0; A[14] = 0.0; A[15] = 1.0;
-}
-
 __global__ void __launch_bounds__(PM_ICP_GPTS)
 pm_icp_nn_grid_kernel(const double *__restrict__ cur, int n1, const double *__restrict__ fixed,
                       const PmIcpGrid *__restrict__ Gp, const int *__restrict__ cell_start,
                       const double *__restrict__ sorted_pts, const int *__restrict__ sorted_idx,
-                      const double *__restrict__ shift, int32_t *__restrict__ nn, double *__restrict__ partial) {
+                      const double *__restrict__ shift, int transform, int32_t *__restrict__ nn,
+                      double *__restrict__ partial) {
     __shared__ double sums[PM_ICP_GPTS][PM_ICP_NSUM + 1];
     const PmIcpGrid G = *Gp;
     const int i = blockIdx.x * PM_ICP_GPTS + threadIdx.x;
@@ -390,17 +398,7 @@ pm_icp_nn_grid_kernel(const double *__restrict__ cur, int n1, const double *__re
     if (live) {
         if (bj == 0x7fffffff) bj = 0;            // no finite distance at all: np.argmin of an all-NaN row
         nn[i] = bj;
-        const double m[4] = {mx - shift[0], my - shift[1], mz - shift[2], 1.0};
-        const double f[3] = {fixed[3 * (size_t)bj], fixed[3 * (size_t)bj + 1], fixed[3 * (size_t)bj + 2]};
-        int q = 0;
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = a; b < 4; ++b) v[q++] = m[a] * m[b];
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) v[q++] = f[a] * m[b];
+        pm_icp_terms(mx, my, mz, shift, fixed, bj, transform, v);
     }
 #pragma unroll
     for (int q = 0; q < PM_ICP_NSUM; ++q) sums[threadIdx.x][q] = v[q];
@@ -418,9 +416,9 @@ pm_icp_nn_grid_kernel(const double *__restrict__ cur, int n1, const double *__re
 // the partials in the same fixed order and solves the 4x4 system itself (redundantly: cheaper than a second
 // barrier and a broadcast) -> apply, residual partials.  The partial sums ping-pong between two buffers, so
 // a CTA that runs ahead into the next iteration cannot overwrite what a slower one still reads.
-__global__ void __launch_bounds__(PM_ICP_QPB * PM_ICP_LPQ)
+__global__ void __launch_bounds__(PM_ICP_QPB * PM_ICP_LPQ, 4)     // <= 128 registers: 4 CTAs per SM stay co-resident (20k clouds)
 pm_icp_persistent_kernel(const double *__restrict__ moving, int n1, const double *__restrict__ fixed, int iterations,
-                         const PmIcpGrid *__restrict__ Gp, const int *__restrict__ cell_start,
+                         int transform, const PmIcpGrid *__restrict__ Gp, const int *__restrict__ cell_start,
                          const double *__restrict__ sorted_pts, const int *__restrict__ sorted_idx,
                          int32_t *__restrict__ nn, double *__restrict__ partial /* [2][grid][NSUM] */,
                          double *__restrict__ res_partial /* [iterations][grid] */, double *__restrict__ a_icp_out) {
@@ -451,7 +449,7 @@ pm_icp_persistent_kernel(const double *__restrict__ moving, int n1, const double
         pm_icp_grid_search<PM_ICP_LPQ>(G, cell_start, sorted_pts, sorted_idx, mx, my, mz, bd, bj);
         if (live) {
             if (bj == 0x7fffffff) bj = 0;        // no finite distance at all: np.argmin of an all-NaN row
-            pm_icp_terms(mx, my, mz, shift, fixed, bj, v);
+            pm_icp_terms(mx, my, mz, shift, fixed, bj, transform, v);
         }
         if (lead) {
 #pragma unroll
@@ -479,7 +477,7 @@ pm_icp_persistent_kernel(const double *__restrict__ moving, int n1, const double
             tot[threadIdx.x] = (((sums[0][threadIdx.x] + sums[1][threadIdx.x]) + sums[2][threadIdx.x]) + sums[3][threadIdx.x]) +
                                sums[4][threadIdx.x];
         __syncthreads();
-        if (threadIdx.x == 0) pm_icp_solve_terms(tot, shift, s_a);
+        if (threadIdx.x == 0) pm_icp_solve_terms(tot, shift, fixed, transform, s_a);
         __syncthreads();
         double r = 0.0;
         if (live) {     // apply (apply_transform.py:14-17), residual against this iteration's matches (utils.py:77-88)
@@ -511,6 +509,7 @@ pm_icp_persistent_kernel(const double *__restrict__ moving, int n1, const double
 // One CTA: reduce partials, solve, compose.  A_est -> a_est[16]; a_icp <- A_est @ a_icp.
 __global__ void __launch_bounds__(256) pm_icp_solve_kernel(const double *__restrict__ partial, int nblocks,
                                                            const double *__restrict__ shift,
+                                                           const double *__restrict__ fixed, int transform,
                                                            double *__restrict__ a_est, double *__restrict__ a_icp) {
     __shared__ double tot[PM_ICP_NSUM];
     __shared__ double red[8][PM_ICP_NSUM];
@@ -528,20 +527,8 @@ __global__ void __launch_bounds__(256) pm_icp_solve_kernel(const double *__restr
     }
     __syncthreads();
     if (threadIdx.x != 0) return;
-    double M[16], X[12], A[16];
-    int k = 0;
-    for (int a = 0; a < 4; ++a)
-        for (int b = a; b < 4; ++b) { M[a * 4 + b] = tot[k]; M[b * 4 + a] = tot[k]; ++k; }
-    const bool ok = pm_solve_right_4x4(M, tot + 10, 3, X, 1e-14);
-    for (int r = 0; r < 3; ++r) {
-        if (ok) {
-            A[r * 4 + 0] = X[r * 4 + 0]; A[r * 4 + 1] = X[r * 4 + 1]; A[r * 4 + 2] = X[r * 4 + 2];
-            A[r * 4 + 3] = X[r * 4 + 3] - (X[r * 4 + 0] * shift[0] + X[r * 4 + 1] * shift[1] + X[r * 4 + 2] * shift[2]);
-        } else {
-            for (int c = 0; c < 4; ++c) A[r * 4 + c] = nan("");
-        }
-    }
-    A[12] = 0.0; A[13] = 0.0; A[14] = 0.0; A[15] = 1.0;
+    double A[16];
+    pm_icp_solve_terms(tot, shift, fixed, transform, A);
     double C[16];
     for (int r = 0; r < 4; ++r)
         for (int c = 0; c < 4; ++c) {
@@ -621,14 +608,15 @@ extern "C" size_t pm_icp_workspace_bytes2(int n1, int n2) {
 
 extern "C" size_t pm_icp_workspace_bytes(int n1) { return pm_icp_workspace_bytes2(n1, 0 + 1) - pm_icp_grid_bytes(1); }
 
-extern "C" int pm_icp_affine(const double *moving, int n1, const double *fixed, int n2, int iterations,
-                             double *A_icp, double *residuals, int32_t *nn_out, void *workspace,
-                             size_t workspace_bytes, void *stream) {
+extern "C" int pm_icp(const double *moving, int n1, const double *fixed, int n2, int iterations, int transform,
+                      double *A_icp, double *residuals, int32_t *nn_out, void *workspace, size_t workspace_bytes,
+                      void *stream) {
     PM_REQUIRE(moving && fixed && A_icp && workspace, "null pointer");
-    PM_REQUIRE(n1 >= 4 && n2 >= 1, "need n1 >= 4 and n2 >= 1");
+    PM_REQUIRE(n1 >= 1 && n2 >= 1, "need n1 >= 1 and n2 >= 1");
+    PM_REQUIRE(transform == PM_TRANSFORM_AFFINE || transform == PM_TRANSFORM_SIMILAR, "unknown transform");
     PM_REQUIRE(iterations >= 0 && iterations <= 1024, "iterations must be 0..1024");
     if (workspace_bytes < pm_icp_workspace_bytes(n1)) {
-        pm_set_error("pm_icp_affine: workspace too small");
+        pm_set_error("pm_icp: workspace too small");
         return PM_ERR_WORKSPACE;
     }
     // the grid search needs the larger workspace of pm_icp_workspace_bytes2 (and pays off from a few hundred points)
@@ -669,7 +657,7 @@ extern "C" int pm_icp_affine(const double *moving, int n1, const double *fixed, 
         PM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm_icp_persistent_kernel, PM_ICP_QPB * PM_ICP_LPQ, 0));
         if (nb_pers <= sms * per_sm) {
             double *a_out = a_icp;
-            void *args[] = {(void *)&moving, (void *)&n1, (void *)&fixed, (void *)&iterations, (void *)&grid, (void *)&cell_start,
+            void *args[] = {(void *)&moving, (void *)&n1, (void *)&fixed, (void *)&iterations, (void *)&transform, (void *)&grid, (void *)&cell_start,
                             (void *)&sorted_pts, (void *)&sorted_idx, (void *)&nn, (void *)&partial, (void *)&res_partial,
                             (void *)&a_out};
             PM_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)pm_icp_persistent_kernel, dim3(nb_pers),
@@ -690,10 +678,10 @@ extern "C" int pm_icp_affine(const double *moving, int n1, const double *fixed, 
     for (int it = 0; it < iterations; ++it) {
         if (use_grid)
             pm_icp_nn_grid_kernel<<<nb_grid, PM_ICP_GPTS, 0, s>>>(cur, n1, fixed, grid, cell_start, sorted_pts, sorted_idx,
-                                                                  shift, nn, partial);
+                                                                  shift, transform, nn, partial);
         else
-            pm_icp_nn_kernel<<<nb_nn, PM_ICP_PTS * PM_ICP_SLICES, 0, s>>>(cur, n1, fixed, n2, shift, nn, partial);
-        pm_icp_solve_kernel<<<1, 256, 0, s>>>(partial, use_grid ? nb_grid : nb_nn, shift, a_est, a_icp);
+            pm_icp_nn_kernel<<<nb_nn, PM_ICP_PTS * PM_ICP_SLICES, 0, s>>>(cur, n1, fixed, n2, shift, transform, nn, partial);
+        pm_icp_solve_kernel<<<1, 256, 0, s>>>(partial, use_grid ? nb_grid : nb_nn, shift, fixed, transform, a_est, a_icp);
         pm_icp_apply_kernel<<<nb_ap, 256, 0, s>>>(cur, n1, fixed, nn, a_est, res_partial + (size_t)it * nb_ap);
     }
     PM_LAUNCH_CHECK_N(3 * iterations);
@@ -705,4 +693,11 @@ extern "C" int pm_icp_affine(const double *moving, int n1, const double *fixed, 
     if (nn_out && iterations > 0)
         PM_CUDA_TRY(cudaMemcpyAsync(nn_out, nn, (size_t)n1 * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
     return PM_OK;
+}
+
+extern "C" int pm_icp_affine(const double *moving, int n1, const double *fixed, int n2, int iterations,
+                             double *A_icp, double *residuals, int32_t *nn_out, void *workspace,
+                             size_t workspace_bytes, void *stream) {
+    return pm_icp(moving, n1, fixed, n2, iterations, PM_TRANSFORM_AFFINE, A_icp, residuals, nn_out, workspace,
+                  workspace_bytes, stream);
 }

@@ -1230,6 +1230,27 @@ __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmL
 }
 
 // ------------------------------------------------------------------------------------- host
+// A kernel's MaxDynamicSharedMemorySize attribute is process-global state: setting it to the per-call size
+// right before each launch races when several host threads solve problems of different sizes (another thread
+// can lower it between this thread's SetAttribute and its launch -> "invalid argument").  Raise it ONCE per
+// device to the opt-in maximum instead and never lower it.
+#include <mutex>
+static int pm_lap_raise_smem_limit_impl(const void *kernel, int smem_optin, int dev) {
+    static std::mutex mu;
+    static const void *seen_kernel[64];
+    static int seen_dev[64], n_seen = 0;
+    std::lock_guard<std::mutex> g(mu);
+    for (int q = 0; q < n_seen; ++q)
+        if (seen_kernel[q] == kernel && seen_dev[q] == dev) return PM_OK;
+    PM_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+    if (n_seen < 64) { seen_kernel[n_seen] = kernel; seen_dev[n_seen] = dev; ++n_seen; }
+    return PM_OK;
+}
+template <typename K>
+static int pm_lap_raise_smem_limit(K kernel, int smem_optin, int dev) {
+    return pm_lap_raise_smem_limit_impl((const void *)kernel, smem_optin, dev);
+}
+
 extern "C" size_t pm_lap_workspace_bytes(int batch, int nr, int nc) {
     if (batch < 1 || nr < 1 || nc < 1) return 0;
     const int ncp = (nc + 3) & ~3;
@@ -1237,9 +1258,9 @@ extern "C" size_t pm_lap_workspace_bytes(int batch, int nr, int nc) {
 }
 
 template <int CPT, bool VR>
-static int pm_lap_launch_sap(const PmLapBatch &B, int batch, int threads, cudaStream_t s) {
+static int pm_lap_launch_sap(const PmLapBatch &B, int batch, int threads, int smem_optin, int dev, cudaStream_t s) {
     const size_t smem = (size_t)(CPT / 4) * threads * 4 * 2 * sizeof(int32_t);
-    PM_CUDA_TRY(cudaFuncSetAttribute(pm_lap_sap_kernel<CPT, VR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = pm_lap_raise_smem_limit(pm_lap_sap_kernel<CPT, VR>, smem_optin, dev)) return rc;
     pm_lap_sap_kernel<CPT, VR><<<batch, threads, smem, s>>>(B, 0);
     PM_LAUNCH_CHECK();
     return PM_OK;
@@ -1328,7 +1349,7 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
         // 1024-thread CTAs (a batch of matrices) are never placed on the same SM
         size_t tail_smem = ls_smem;
         if (tail_smem < 120 * 1024 && (size_t)smem_optin >= 120 * 1024 + 2048) tail_smem = 120 * 1024;
-        PM_CUDA_TRY(cudaFuncSetAttribute(pm_ls_auction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
+        if (int rc = pm_lap_raise_smem_limit(pm_ls_auction_kernel, smem_optin, dev)) return rc;
         pm_ls_auction_kernel<<<batch, 1024, tail_smem, s>>>(B);
         PM_LAUNCH_CHECK();
     } else if (max_bid_rounds > 0) {
@@ -1347,7 +1368,7 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
     const size_t ss_smem = (size_t)B.ncp * (8 + 8 + 2 + 2 + 2 + 1);
     if (max_bid_rounds > 0 && algorithm == PM_LAP_ALGO_SPARSE_AUCTION && ss_smem + 2048 <= (size_t)smem_optin &&
         !getenv("PM_LAP_DENSE_SAP")) {
-        PM_CUDA_TRY(cudaFuncSetAttribute(pm_lap_sap_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss_smem));
+        if (int rc = pm_lap_raise_smem_limit(pm_lap_sap_sparse_kernel, smem_optin, dev)) return rc;
         pm_lap_sap_sparse_kernel<<<batch, PM_SS_THREADS, ss_smem, s>>>(B);
         PM_LAUNCH_CHECK();
         rc = PM_OK;
@@ -1355,11 +1376,11 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
         int threads = ((nc + PM_LAP_CPT - 1) / PM_LAP_CPT + 31) & ~31;
         if (threads < 64) threads = 64;
         if (threads > PM_LAP_MAX_THREADS) threads = PM_LAP_MAX_THREADS;
-        rc = pm_lap_launch_sap<PM_LAP_CPT, true>(B, batch, threads, s);
+        rc = pm_lap_launch_sap<PM_LAP_CPT, true>(B, batch, threads, smem_optin, dev, s);
     } else if (nc <= 16 * PM_LAP_MAX_THREADS) {
-        rc = pm_lap_launch_sap<16, false>(B, batch, PM_LAP_MAX_THREADS, s);
+        rc = pm_lap_launch_sap<16, false>(B, batch, PM_LAP_MAX_THREADS, smem_optin, dev, s);
     } else {
-        rc = pm_lap_launch_sap<24, false>(B, batch, PM_LAP_MAX_THREADS, s);
+        rc = pm_lap_launch_sap<24, false>(B, batch, PM_LAP_MAX_THREADS, smem_optin, dev, s);
     }
     return rc;
 }

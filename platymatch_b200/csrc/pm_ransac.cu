@@ -11,8 +11,10 @@
 // (Gauss-Jordan with partial pivoting; K > 4 samples go through the normal equations),
 // (2) one warp per trial scores it against all correspondences staged through shared memory,
 // (3) one CTA picks the maximum inlier count with the lowest trial index.
-// Degenerate samples (numerically singular 4x4, where numpy's pinv would still return a
-// minimum-norm answer) are scored as 0 inliers and counted in stats.
+// Degenerate samples (numerically singular 4x4: coplanar points, flat 2-D data) get numpy's answer for them, the
+// minimum-norm least-squares affine of pinv (pm_linalg.cuh), so planar clouds register like in the reference.
+// transform = PM_TRANSFORM_SIMILAR fits Horn's similarity (get_similar_transform, find_transform.py:21-99) instead
+// (shape_context.py:128-129).
 #include "pm_common.cuh"
 
 // ---- Philox4x32-10 counter RNG (device-side sampling when no index stream is given) ----
@@ -38,7 +40,7 @@ __device__ inline void pm_philox4(unsigned long long seed, uint32_t ctr0, uint32
 // hyp[t][0:12] = rows 0..2 of A; hyp[t][12] = 1 if valid else 0
 __global__ void pm_ransac_hypotheses(const double *__restrict__ moving, const double *__restrict__ fixed, int k,
                                      const int32_t *__restrict__ sample_idx, int trials, int min_samples,
-                                     unsigned long long seed, double *__restrict__ hyp,
+                                     unsigned long long seed, int transform, double *__restrict__ hyp,
                                      int32_t *__restrict__ drawn_idx) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= trials) return;
@@ -60,33 +62,67 @@ __global__ void pm_ransac_hypotheses(const double *__restrict__ moving, const do
     }
     if (drawn_idx)
         for (int s = 0; s < min_samples; ++s) drawn_idx[(size_t)t * min_samples + s] = idx[s];
-    double M[16], R[12], X[12];
+    double A[16];
     bool ok = true;
     for (int s = 0; s < min_samples; ++s) ok &= (idx[s] >= 0 && idx[s] < k);
-    if (ok) {
+    if (ok && transform == PM_TRANSFORM_SIMILAR) {
+        // get_similar_transform (find_transform.py:21-99) on the sampled pairs: centroids, centred moments, Horn
+        double cp[3] = {0.0, 0.0, 0.0}, cy[3] = {0.0, 0.0, 0.0};
+        for (int s = 0; s < min_samples; ++s) {
+            const double *m = moving + 3 * (size_t)idx[s], *f = fixed + 3 * (size_t)idx[s];
+            for (int a = 0; a < 3; ++a) { cp[a] += m[a]; cy[a] += f[a]; }
+        }
+        for (int a = 0; a < 3; ++a) { cp[a] /= min_samples; cy[a] /= min_samples; }
+        double S[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, spp = 0.0, syy = 0.0;
+        for (int s = 0; s < min_samples; ++s) {
+            const double *m = moving + 3 * (size_t)idx[s], *f = fixed + 3 * (size_t)idx[s];
+            const double pc[3] = {m[0] - cp[0], m[1] - cp[1], m[2] - cp[2]};
+            const double yc[3] = {f[0] - cy[0], f[1] - cy[1], f[2] - cy[2]};
+            for (int a = 0; a < 3; ++a) {
+                for (int b = 0; b < 3; ++b) S[a * 3 + b] += pc[a] * yc[b];
+                spp += pc[a] * pc[a];
+                syy += yc[a] * yc[a];
+            }
+        }
+        pm_similar_from_moments(cp, cy, S, spp, syy, A);
+    } else if (ok) {
+        double M[16], R[12], X[12];
+        bool solved = false;
         if (min_samples == 4) {
-            // A M_h = F  with M_h columns = [m_s; 1]
+            // A M_h = F  with M_h columns = [m_s; 1]: exact solve
             for (int s = 0; s < 4; ++s) {
                 const double *m = moving + 3 * (size_t)idx[s], *f = fixed + 3 * (size_t)idx[s];
                 M[0 * 4 + s] = m[0]; M[1 * 4 + s] = m[1]; M[2 * 4 + s] = m[2]; M[3 * 4 + s] = 1.0;
                 R[0 * 4 + s] = f[0]; R[1 * 4 + s] = f[1]; R[2 * 4 + s] = f[2];
             }
-        } else {
+            solved = pm_solve_right_4x4(M, R, 3, X, 1e-13);
+            if (solved) {
+                for (int q = 0; q < 12; ++q) A[q] = X[q];
+                A[12] = 0.0; A[13] = 0.0; A[14] = 0.0; A[15] = 1.0;
+            }
+        }
+        if (!solved) {
+            // more (or fewer) than 4 samples, or a degenerate (coplanar) 4-sample: least squares through the normal
+            // equations, pinv's minimum-norm answer when they are singular (find_transform.py:17)
+            const double *m0 = moving + 3 * (size_t)idx[0];
+            const double shift[3] = {m0[0], m0[1], m0[2]};
             for (int q = 0; q < 16; ++q) M[q] = 0.0;
             for (int q = 0; q < 12; ++q) R[q] = 0.0;
             for (int s = 0; s < min_samples; ++s) {
                 const double *m = moving + 3 * (size_t)idx[s], *f = fixed + 3 * (size_t)idx[s];
-                const double mh[4] = {m[0], m[1], m[2], 1.0};
+                const double mh[4] = {m[0] - shift[0], m[1] - shift[1], m[2] - shift[2], 1.0};
                 for (int a = 0; a < 4; ++a)
                     for (int b = 0; b < 4; ++b) M[a * 4 + b] += mh[a] * mh[b];
                 for (int a = 0; a < 3; ++a)
                     for (int b = 0; b < 4; ++b) R[a * 4 + b] += f[a] * mh[b];
             }
+            pm_affine_from_normal_eq(M, R, shift, 1e-13, A);
         }
-        ok = pm_solve_right_4x4(M, R, 3, X, 1e-13);
     }
+    if (ok)
+        for (int q = 0; q < 12; ++q) ok &= isfinite(A[q]);
     double *h = hyp + (size_t)t * 13;
-    for (int q = 0; q < 12; ++q) h[q] = ok ? X[q] : 0.0;
+    for (int q = 0; q < 12; ++q) h[q] = ok ? A[q] : 0.0;
     h[12] = ok ? 1.0 : 0.0;
 }
 
@@ -181,23 +217,24 @@ extern "C" size_t pm_ransac_workspace_bytes(int trials) {
     return (size_t)trials * 13 * sizeof(double) + (size_t)trials * sizeof(int32_t) + 64;
 }
 
-extern "C" int pm_ransac_affine(const double *moving, const double *fixed, int k, const int32_t *sample_idx,
-                                int trials, int min_samples, double error, unsigned long long seed, double *best_A,
-                                int32_t *best_inliers, int32_t *best_trial, int32_t *inliers_per_trial,
-                                void *workspace, size_t workspace_bytes, void *stream) {
+extern "C" int pm_ransac(const double *moving, const double *fixed, int k, const int32_t *sample_idx, int trials,
+                         int min_samples, double error, unsigned long long seed, int transform, double *best_A,
+                         int32_t *best_inliers, int32_t *best_trial, int32_t *inliers_per_trial, void *workspace,
+                         size_t workspace_bytes, void *stream) {
     PM_REQUIRE(moving && fixed && best_A && best_inliers && best_trial && workspace, "null pointer");
     PM_REQUIRE(trials >= 1, "need at least one trial");
-    PM_REQUIRE(min_samples >= 4 && min_samples <= PM_RANSAC_MAX_SAMPLES, "min_samples must be 4..16");
+    PM_REQUIRE(transform == PM_TRANSFORM_AFFINE || transform == PM_TRANSFORM_SIMILAR, "unknown transform");
+    PM_REQUIRE(min_samples >= 1 && min_samples <= PM_RANSAC_MAX_SAMPLES, "min_samples must be 1..16");
     PM_REQUIRE(k >= min_samples, "fewer correspondences than samples");
     if (workspace_bytes < pm_ransac_workspace_bytes(trials)) {
-        pm_set_error("pm_ransac_affine: workspace too small");
+        pm_set_error("pm_ransac: workspace too small");
         return PM_ERR_WORKSPACE;
     }
     cudaStream_t s = pm_stream(stream);
     double *hyp = (double *)workspace;
     int32_t *inl = inliers_per_trial ? inliers_per_trial : (int32_t *)(hyp + (size_t)trials * 13);
     pm_ransac_hypotheses<<<(trials + 127) / 128, 128, 0, s>>>(moving, fixed, k, sample_idx, trials, min_samples, seed,
-                                                             hyp, nullptr);
+                                                             transform, hyp, nullptr);
     PM_LAUNCH_CHECK();
     pm_ransac_score<<<(trials + PM_RANSAC_WARPS - 1) / PM_RANSAC_WARPS, PM_RANSAC_WARPS * 32, 0, s>>>(
         moving, fixed, k, hyp, trials, error, inl);
@@ -205,4 +242,12 @@ extern "C" int pm_ransac_affine(const double *moving, const double *fixed, int k
     pm_ransac_select<<<1, 1024, 0, s>>>(inl, hyp, trials, best_A, best_inliers, best_trial);
     PM_LAUNCH_CHECK();
     return PM_OK;
+}
+
+extern "C" int pm_ransac_affine(const double *moving, const double *fixed, int k, const int32_t *sample_idx,
+                                int trials, int min_samples, double error, unsigned long long seed, double *best_A,
+                                int32_t *best_inliers, int32_t *best_trial, int32_t *inliers_per_trial,
+                                void *workspace, size_t workspace_bytes, void *stream) {
+    return pm_ransac(moving, fixed, k, sample_idx, trials, min_samples, error, seed, PM_TRANSFORM_AFFINE, best_A,
+                     best_inliers, best_trial, inliers_per_trial, workspace, workspace_bytes, stream);
 }

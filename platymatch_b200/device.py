@@ -7,9 +7,17 @@ fused pipeline (pipeline.py) are built from these.
 import numpy as np
 
 from . import _lib
-from ._lib import NBINS, LAP_STATS, CHI2_TILE, check, ptr, stream_ptr, load
+from ._lib import NBINS, LAP_STATS, CHI2_TILE, TRANSFORMS, check, ptr, stream_ptr, load
 
 R_EDGES = np.logspace(np.log10(1 / 8), np.log10(2), 5)  # shape_context.py:24 — numpy's exact doubles
+
+
+def transform_code(transform):
+    """The widget's transform string ('Affine' / 'Similar', _dock_widget.py:627) -> PM_TRANSFORM_*."""
+    try:
+        return TRANSFORMS[transform]
+    except KeyError:
+        raise ValueError("transform must be 'Affine' or 'Similar', got %r" % (transform,))
 
 
 def _torch():
@@ -116,16 +124,21 @@ def chi2_cost(a, b, out=None, row_begin=0, row_end=None):
     return out
 
 
-def lap_solve(cost, nr, nc, max_bid_rounds=2048, algorithm=0):
-    """cost [batch, nr, ldc] float32 (nr <= nc) -> col4row [batch, nr] int32, total [batch] f64, stats [batch, 8] i64."""
+def lap_solve(cost, nr, nc, max_bid_rounds=2048, algorithm=0, out=None):
+    """cost [batch, nr, ldc] float32 (nr <= nc) -> col4row [batch, nr] int32, total [batch] f64, stats [batch, 16] i64.
+    out = (col4row, total, stats) writes into caller-owned tensors (views of a larger batch are fine)."""
     torch = _torch()
     if cost.dim() == 2:
         cost = cost.unsqueeze(0)
     batch, ldc = cost.shape[0], cost.stride(1)
-    assert cost.stride(2) == 1 and cost.stride(0) == nr * ldc, "cost batch must be densely stacked"
-    col4row = torch.empty((batch, nr), dtype=torch.int32, device=cost.device)
-    total = torch.empty(batch, dtype=torch.float64, device=cost.device)
-    stats = torch.zeros((batch, LAP_STATS), dtype=torch.int64, device=cost.device)
+    assert cost.stride(2) == 1 and (batch == 1 or cost.stride(0) == nr * ldc), "cost batch must be densely stacked"
+    if out is None:
+        col4row = torch.empty((batch, nr), dtype=torch.int32, device=cost.device)
+        total = torch.empty(batch, dtype=torch.float64, device=cost.device)
+        stats = torch.empty((batch, LAP_STATS), dtype=torch.int64, device=cost.device)     # zeroed by the init kernel
+    else:
+        col4row, total, stats = out
+        assert col4row.is_contiguous() and total.is_contiguous() and stats.is_contiguous()
     nbytes = load().pm_lap_workspace_bytes(batch, nr, nc)
     ws = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=cost.device)
     check(load().pm_lap_solve(ptr(cost), batch, nr, nc, ldc, int(max_bid_rounds), int(algorithm), ptr(col4row), ptr(total), ptr(stats),
@@ -133,13 +146,18 @@ def lap_solve(cost, nr, nc, max_bid_rounds=2048, algorithm=0):
     return col4row, total, stats
 
 
-def ransac_affine(moving_k, fixed_k, trials, error, min_samples=4, sample_idx=None, seed=0, want_per_trial=False):
-    """moving_k / fixed_k [K,3] in correspondence order -> (A [16], inliers [1] i32, trial [1] i32, per_trial|None)."""
+def ransac(moving_k, fixed_k, trials, error, min_samples=4, sample_idx=None, seed=0, want_per_trial=False,
+           transform='Affine', out=None):
+    """moving_k / fixed_k [K,3] in correspondence order -> (A [16], inliers [1] i32, trial [1] i32, per_trial|None).
+    out = (A [16] f64, inliers [1] i32) writes the first two results into caller-owned tensors."""
     torch = _torch()
     k = moving_k.shape[0]
     dev = moving_k.device
-    best_a = torch.empty(16, dtype=torch.float64, device=dev)
-    best_inl = torch.empty(1, dtype=torch.int32, device=dev)
+    if out is None:
+        best_a = torch.empty(16, dtype=torch.float64, device=dev)
+        best_inl = torch.empty(1, dtype=torch.int32, device=dev)
+    else:
+        best_a, best_inl = out
     best_trial = torch.empty(1, dtype=torch.int32, device=dev)
     per_trial = torch.empty(trials, dtype=torch.int32, device=dev) if want_per_trial else None
     if sample_idx is not None:
@@ -147,13 +165,17 @@ def ransac_affine(moving_k, fixed_k, trials, error, min_samples=4, sample_idx=No
         assert tuple(sample_idx.shape) == (trials, min_samples)
     nbytes = load().pm_ransac_workspace_bytes(trials)
     ws = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=dev)
-    check(load().pm_ransac_affine(ptr(moving_k), ptr(fixed_k), k, ptr(sample_idx), trials, min_samples, float(error),
-                                  int(seed) & (2 ** 64 - 1), ptr(best_a), ptr(best_inl), ptr(best_trial),
-                                  ptr(per_trial), ptr(ws), nbytes, stream_ptr()), "pm_ransac_affine")
+    check(load().pm_ransac(ptr(moving_k), ptr(fixed_k), k, ptr(sample_idx), trials, min_samples, float(error),
+                           int(seed) & (2 ** 64 - 1), transform_code(transform), ptr(best_a), ptr(best_inl),
+                           ptr(best_trial), ptr(per_trial), ptr(ws), nbytes, stream_ptr()), "pm_ransac")
     return best_a, best_inl, best_trial, per_trial
 
 
-def icp_affine(moving, fixed, iterations=50, want_nn=False):
+def ransac_affine(moving_k, fixed_k, trials, error, min_samples=4, sample_idx=None, seed=0, want_per_trial=False):
+    return ransac(moving_k, fixed_k, trials, error, min_samples, sample_idx, seed, want_per_trial, 'Affine')
+
+
+def icp(moving, fixed, iterations=50, want_nn=False, transform='Affine'):
     """-> (A_icp [16] f64, residuals [iterations] f64, nn [N1] i32 | None)."""
     torch = _torch()
     n1, n2, dev = moving.shape[0], fixed.shape[0], moving.device
@@ -162,16 +184,39 @@ def icp_affine(moving, fixed, iterations=50, want_nn=False):
     nn = torch.empty(n1, dtype=torch.int32, device=dev) if want_nn else None
     nbytes = load().pm_icp_workspace_bytes2(n1, n2)
     ws = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=dev)
-    check(load().pm_icp_affine(ptr(moving), n1, ptr(fixed), n2, int(iterations), ptr(a_icp), ptr(resid), ptr(nn),
-                               ptr(ws), nbytes, stream_ptr()), "pm_icp_affine")
+    check(load().pm_icp(ptr(moving), n1, ptr(fixed), n2, int(iterations), transform_code(transform), ptr(a_icp),
+                        ptr(resid), ptr(nn), ptr(ws), nbytes, stream_ptr()), "pm_icp")
     return a_icp, resid[:iterations], nn
 
 
-def fit_affine(moving_k, fixed_k):
+def icp_affine(moving, fixed, iterations=50, want_nn=False):
+    return icp(moving, fixed, iterations, want_nn, 'Affine')
+
+
+def fit_transform(moving_k, fixed_k, transform='Affine'):
+    """get_affine_transform / get_similar_transform (find_transform.py:4-17, :21-99) on [K,3] pairs -> [16] f64."""
     torch = _torch()
     a = torch.empty(16, dtype=torch.float64, device=moving_k.device)
-    check(load().pm_fit_affine(ptr(moving_k), ptr(fixed_k), moving_k.shape[0], ptr(a), stream_ptr()), "pm_fit_affine")
+    if transform_code(transform) == TRANSFORMS['Similar']:
+        check(load().pm_fit_similar(ptr(moving_k), ptr(fixed_k), moving_k.shape[0], ptr(a), stream_ptr()), "pm_fit_similar")
+    else:
+        check(load().pm_fit_affine(ptr(moving_k), ptr(fixed_k), moving_k.shape[0], ptr(a), stream_ptr()), "pm_fit_affine")
     return a
+
+
+def select_best(inliers, a_all):
+    """np.argmax(inliers) on the device (_dock_widget.py:683): -> (best [1] i32, A_best [16] f64)."""
+    torch = _torch()
+    n = inliers.numel()
+    assert inliers.dtype == torch.int32 and a_all.is_contiguous() and a_all.numel() == 16 * n
+    best = torch.empty(1, dtype=torch.int32, device=inliers.device)
+    a = torch.empty(16, dtype=torch.float64, device=inliers.device)
+    check(load().pm_select_best(ptr(inliers), ptr(a_all), n, ptr(best), ptr(a), stream_ptr()), "pm_select_best")
+    return best, a
+
+
+def fit_affine(moving_k, fixed_k):
+    return fit_transform(moving_k, fixed_k, 'Affine')
 
 
 def apply_affine(pts, a16):

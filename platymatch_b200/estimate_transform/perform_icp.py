@@ -11,11 +11,9 @@ def perform_icp(moving, fixed, icp_iterations=50, transform='Affine', verbose=Tr
 
     The reference prints the mean residual of every iteration (:24); `verbose` keeps that behaviour.
     """
-    if transform != 'Affine':
-        raise NotImplementedError("transform='Similar' is a SURVEY §8(f) 'next' row; only 'Affine' is built")
     m = D.to_device_points(moving)
     f = D.to_device_points(fixed)
-    a_icp, resid, _ = D.icp_affine(m, f, int(icp_iterations))
+    a_icp, resid, _ = D.icp(m, f, int(icp_iterations), transform=transform)       # 'Affine' | 'Similar' (:17-20)
     resid = resid.cpu().numpy()
     if verbose:
         for i, r in enumerate(resid):

@@ -70,8 +70,7 @@ def do_ransac(moving_all, fixed_all, min_samples=4, trials=500, error=5, transfo
     fresh entropy) or from an explicit (trials, min_samples) index array (`sample_indices`), which is
     what the parity tests use.
     """
-    if transform != 'Affine':
-        raise NotImplementedError("transform='Similar' is a SURVEY §8(f) 'next' row; only 'Affine' is built")
+    D.transform_code(transform)          # 'Affine' or 'Similar' (:126-129); anything else raises ValueError
     torch = D._torch()
     m = D.to_device_points(moving_all)
     f = D.to_device_points(fixed_all)
@@ -81,5 +80,5 @@ def do_ransac(moving_all, fixed_all, min_samples=4, trials=500, error=5, transfo
         trials = idx.shape[0]
     if seed is None:
         seed = int(np.random.SeedSequence().entropy & (2 ** 63 - 1))
-    a, inl, _, _ = D.ransac_affine(m, f, int(trials), float(error), int(min_samples), idx, seed)
+    a, inl, _, _ = D.ransac(m, f, int(trials), float(error), int(min_samples), idx, seed, transform=transform)
     return a.cpu().numpy().reshape(4, 4), int(inl.item())

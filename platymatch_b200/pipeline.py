@@ -11,7 +11,7 @@ from . import device as D
 from ._lib import LAP_STATS as _LAP_STATS
 
 __all__ = ["HYPOTHESES_REFERENCE", "HYPOTHESES_DISTINCT", "estimate_transform_unsupervised",
-           "estimate_transform_supervised", "Descriptors", "describe_cloud", "register_described"]
+           "estimate_transform_supervised", "Descriptors", "describe_cloud", "describe_pair", "register_described"]
 
 # (moving variant a, fixed variant b) of U_ab, in the reference's order 11,12,13,14,21,22,23,24
 # (_dock_widget.py:556-602).  sc2/sc3/sc4 are phi-bin permutations of sc, so U21=U12, U22=U11,
@@ -50,6 +50,32 @@ def describe_cloud(cloud, n_variants, transposed=False):
     return Descriptors(pts, stats, md, counts, dropped, ties)
 
 
+_DESC_STREAMS = {}
+
+
+def describe_pair(moving, fixed, n_variants_moving=1, n_variants_fixed=4, transposed=False, overlap=True):
+    """describe_cloud of both clouds; the fixed cloud's kernels run on a side stream next to the moving cloud's
+    (they are independent and neither fills the GPU for long), joined before returning."""
+    torch = D._torch()
+    if not overlap:
+        return describe_cloud(moving, n_variants_moving, transposed), describe_cloud(fixed, n_variants_fixed, transposed)
+    main = torch.cuda.current_stream()
+    key = (torch.cuda.current_device(), main.cuda_stream)
+    side = _DESC_STREAMS.get(key)
+    if side is None:
+        side = _DESC_STREAMS[key] = torch.cuda.Stream()
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        df = describe_cloud(fixed, n_variants_fixed, transposed)
+        for v in range(1, n_variants_fixed + 1):
+            df.operand(v)
+    dm = describe_cloud(moving, n_variants_moving, transposed)
+    for v in range(1, n_variants_moving + 1):
+        dm.operand(v)
+    main.wait_stream(side)
+    return dm, df
+
+
 def _draw_or_take(sample_indices, q):
     if sample_indices is None:
         return None
@@ -75,17 +101,19 @@ def _hypothesis_streams(device, n):
 
 def register_described(dm, df, ransac_samples=4, ransac_trials=8000, ransac_error=16, icp_iterations=50,
                        hypotheses=None, seed=0, sample_indices=None, max_bid_rounds=2048, cost_out=None,
-                       keep_cost=False, stage_hook=None, overlap_hypotheses=True):
+                       keep_cost=False, stage_hook=None, overlap_hypotheses=True, transform='Affine'):
     """Cost matrices -> LAP -> RANSAC -> argmax -> ICP for two described clouds (device resident).
 
     The H hypothesis chains {cost matrix -> assignment -> RANSAC} are independent (reference
     _dock_widget.py:547-675 runs them one after the other).  With `overlap_hypotheses` each chain is enqueued
     on its own CUDA stream: the assignment of one hypothesis is latency-bound on a few SMs and runs underneath
     the compute-bound cost-matrix kernels of the next ones.  Results are identical either way.
-    Returns a dict of CUDA tensors / python scalars; only `best` (one int) is read back in between
-    (the reference's np.argmax over the inlier counts, _dock_widget.py:683-703).
+    Nothing is read back in between: the reference's np.argmax over the inlier counts (_dock_widget.py:683-703)
+    runs on the device (pm_select_best) and ICP takes the winning 4x4 from device memory, so a registration is
+    one uninterrupted stream of launches.  Returns a dict of CUDA tensors (`best` is a 1-element int32 tensor).
     """
     torch = D._torch()
+    D.transform_code(transform)
     hyps = HYPOTHESES_DISTINCT if hypotheses is None else list(hypotheses)
     n1, n2 = dm.n, df.n
     swap = n1 > n2                      # scipy solves the transpose when there are more rows than columns
@@ -99,7 +127,7 @@ def register_described(dm, df, ransac_samples=4, ransac_trials=8000, ransac_erro
     col4row = torch.empty((H, nr), dtype=torch.int32, device=dev)
     lap_total = torch.empty(H, dtype=torch.float64, device=dev)
     lap_stats = torch.empty((H, _LAP_STATS), dtype=torch.int64, device=dev)
-    rows_arange = torch.arange(nr, dtype=torch.int32, device=dev)
+    rows_arange = torch.arange(nr, dtype=torch.int32, device=dev) if swap else None
     pairs = [None] * H
     ops_m = {a: dm.operand(a) for a, _ in hyps}     # built on the caller's stream, before the chains fork
     ops_f = {b: df.operand(b) for _, b in hyps}
@@ -111,23 +139,22 @@ def register_described(dm, df, ransac_samples=4, ransac_trials=8000, ransac_erro
         else:
             D.chi2_cost(ops_m[a], ops_f[b], out=cost[q])
 
-    def assign_and_ransac(q, c4r, tot, st):
-        col4row[q].copy_(c4r)
-        lap_total[q:q + 1].copy_(tot)
-        lap_stats[q].copy_(st)
+    def ransac(q):
         if swap:                        # rows are fixed nuclei; reference order = ascending moving index
             mov_idx, order = torch.sort(col4row[q])
-            fix_idx = rows_arange[order]
-            mov_idx = mov_idx.contiguous()
-        else:
-            mov_idx, fix_idx = rows_arange, col4row[q]
-        mk = D.gather_points(dm.pts, mov_idx)
-        fk = D.gather_points(df.pts, fix_idx.contiguous())
-        a, inl, _, _ = D.ransac_affine(mk, fk, int(ransac_trials), float(ransac_error), int(ransac_samples),
-                                       _draw_or_take(sample_indices, q), seed=(int(seed) << 8) + q)
-        ransac_a[q] = a
-        inliers[q:q + 1] = inl
+            fix_idx = rows_arange[order].contiguous()
+            mk = D.gather_points(dm.pts, mov_idx.contiguous())
+        else:                           # moving[:, row_ind] with row_ind = 0..n1-1 is the cloud itself (:622)
+            mov_idx, fix_idx = None, col4row[q]
+            mk = dm.pts
+        fk = D.gather_points(df.pts, fix_idx)
+        D.ransac(mk, fk, int(ransac_trials), float(ransac_error), int(ransac_samples), _draw_or_take(sample_indices, q),
+                 seed=(int(seed) << 8) + q, transform=transform, out=(ransac_a[q], inliers[q:q + 1]))
         pairs[q] = (mov_idx, fix_idx)
+
+    def lap(q0, q1):
+        D.lap_solve(cost[q0:q1], nr, nc, max_bid_rounds,
+                    out=(col4row[q0:q1], lap_total[q0:q1], lap_stats[q0:q1]))
 
     if overlap_hypotheses and stage_hook is None and H > 1:
         # cost matrices stay on the caller's stream (compute-bound, every SM); each assignment + RANSAC chain
@@ -141,48 +168,73 @@ def register_described(dm, df, ransac_samples=4, ransac_trials=8000, ransac_erro
             ready.record(main)
             side.wait_event(ready)
             with torch.cuda.stream(side):
-                c4r, tot, st = D.lap_solve(cost[q:q + 1], nr, nc, max_bid_rounds)
-                assign_and_ransac(q, c4r[0], tot, st[0])
+                lap(q, q + 1)
+                ransac(q)
         for side in sides:
             main.wait_stream(side)
     else:
         for q in range(H):
             cost_matrix(q)
         if stage_hook: stage_hook("chi2_cost")
-        c4r, tot, st = D.lap_solve(cost, nr, nc, max_bid_rounds)
+        lap(0, H)
         if stage_hook: stage_hook("lap")
         for q in range(H):
-            assign_and_ransac(q, c4r[q], tot[q:q + 1], st[q])
+            ransac(q)
         if stage_hook: stage_hook("ransac")
-    best = int(torch.argmax(inliers).item())     # first maximum, as np.argmax (_dock_widget.py:683)
-    a_sc = ransac_a[best].contiguous()
-    moved = D.apply_affine(dm.pts, a_sc)                                   # :714
-    a_icp, resid, _ = D.icp_affine(moved, df.pts, int(icp_iterations))     # :715-717
-    a_final = D.compose(a_icp, a_sc)                                       # icp @ sc (:428)
+    best, a_sc = D.select_best(inliers, ransac_a)                           # np.argmax, first maximum (:683)
+    moved = D.apply_affine(dm.pts, a_sc)                                    # :714
+    a_icp, resid, _ = D.icp(moved, df.pts, int(icp_iterations), transform=transform)     # :715-717
+    a_final = D.compose(a_icp, a_sc)                                        # icp @ sc (:428)
     if stage_hook: stage_hook("icp")
     out = dict(transform=a_final, transform_sc=a_sc, transform_icp=a_icp, inliers=inliers, ransac_A=ransac_a,
                best=best, hypotheses=hyps, assignments=pairs, lap_cost=lap_total, lap_stats=lap_stats,
-               icp_residuals=resid, edge_ties=(dm.ties, df.ties))
+               icp_residuals=resid, edge_ties=(dm.ties, df.ties), n_moving=n1)
     if keep_cost:
         out["cost"] = cost
     return out
 
 
 def _to_host(res):
+    """One device -> host pass: every result is copied asynchronously into pinned host memory, then the stream is
+    synchronised ONCE (the only host synchronisation of a registration)."""
     torch = D._torch()
-    out = {}
+    pending = []
+
+    def fetch(t):
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        pending.append(h)
+        return h
+
+    staged = {}
     for k, v in res.items():
         if torch.is_tensor(v):
-            v = v.cpu().numpy()
+            staged[k] = fetch(v)
+        elif k == "assignments":
+            staged[k] = [(None if m is None else fetch(m), fetch(f)) for m, f in v]
+        elif k == "edge_ties":
+            staged[k] = tuple(fetch(t) for t in v)
+        else:
+            staged[k] = v
+    torch.cuda.current_stream().synchronize()
+    out = {}
+    for k, v in staged.items():
+        if k == "assignments":
+            n1 = res.get("n_moving")
+            v = [((np.arange(len(f), dtype=np.int64) if m is None else m.numpy().astype(np.int64)),
+                  f.numpy().astype(np.int64)) for m, f in v]
+        elif k == "edge_ties":
+            v = tuple(int(t.item()) for t in v)
+        elif k == "best":
+            v = int(v.item())
+        elif torch.is_tensor(v):
+            v = v.numpy().copy()
             if k.startswith("transform"):
                 v = v.reshape(4, 4)
             elif k == "ransac_A":
                 v = v.reshape(-1, 4, 4)
-        elif k == "assignments":
-            v = [(m.cpu().numpy().astype(np.int64), f.cpu().numpy().astype(np.int64)) for m, f in v]
-        elif k == "edge_ties":
-            v = tuple(int(t.item()) for t in v)
         out[k] = v
+    out.pop("n_moving", None)
     return out
 
 
@@ -197,30 +249,28 @@ def estimate_transform_unsupervised(moving, fixed, *, ransac_samples=4, ransac_t
       icp_residuals, edge_ties.
     `as_reference=True` evaluates all 8 hypotheses like the widget; the default evaluates the 4
     algebraically distinct ones (the other 4 are duplicates up to bin-edge ties).
+    transform: 'Affine' or 'Similar' (the widget's choice, :627) for the RANSAC and ICP fits.
     """
-    if transform != 'Affine':
-        raise NotImplementedError("transform='Similar' is a SURVEY §8(f) 'next' row; only 'Affine' is built")
+    D.transform_code(transform)
     hyps = hypotheses or (HYPOTHESES_REFERENCE if as_reference else HYPOTHESES_DISTINCT)
     need_m = max(a for a, _ in hyps)
     need_f = max(b for _, b in hyps)
-    dm = describe_cloud(moving, 1 if need_m == 1 else 2)
-    df = describe_cloud(fixed, 1 if need_f == 1 else (2 if need_f == 2 else 4))
+    dm, df = describe_pair(moving, fixed, 1 if need_m == 1 else 2, 1 if need_f == 1 else (2 if need_f == 2 else 4))
     res = register_described(dm, df, ransac_samples, ransac_trials, ransac_error, icp_iterations, hyps, seed,
-                             sample_indices, max_bid_rounds, keep_cost=keep_cost)
+                             sample_indices, max_bid_rounds, keep_cost=keep_cost, transform=transform)
     return _to_host(res)
 
 
 def estimate_transform_supervised(moving, fixed, moving_keypoints, fixed_keypoints, *, icp_iterations=50,
                                   transform='Affine'):
-    """Keypoint-supervised registration (reference _dock_widget.py:707-717): least-squares affine on the
-    3xK keypoint pairs, then ICP on the full clouds.  Returns dict(transform, transform_sc, transform_icp,
-    icp_residuals) as numpy arrays."""
-    if transform != 'Affine':
-        raise NotImplementedError("transform='Similar' is a SURVEY §8(f) 'next' row; only 'Affine' is built")
+    """Keypoint-supervised registration (reference _dock_widget.py:707-717): least-squares affine (or Horn
+    similarity, :710-711) on the 3xK keypoint pairs, then ICP on the full clouds.  Returns dict(transform,
+    transform_sc, transform_icp, icp_residuals) as numpy arrays."""
+    D.transform_code(transform)
     m = D.to_device_points(moving)
     f = D.to_device_points(fixed)
-    a_sc = D.fit_affine(D.to_device_points(moving_keypoints), D.to_device_points(fixed_keypoints))
+    a_sc = D.fit_transform(D.to_device_points(moving_keypoints), D.to_device_points(fixed_keypoints), transform)
     moved = D.apply_affine(m, a_sc)
-    a_icp, resid, _ = D.icp_affine(moved, f, int(icp_iterations))
+    a_icp, resid, _ = D.icp(moved, f, int(icp_iterations), transform=transform)
     a_final = D.compose(a_icp, a_sc)
     return _to_host(dict(transform=a_final, transform_sc=a_sc, transform_icp=a_icp, icp_residuals=resid))

@@ -1,0 +1,128 @@
+"""GPU parity at BASELINE.json's OWN configurations: the full oracle pipeline (C/numpy restatement of the
+reference, all host threads) against the CUDA path on the same synthetic pair with one shared RANSAC
+sample-index stream — every stage compared, not only the end result.
+
+  config 1  3k pair  (2700 x 3000)      config 2  8k pair (7200 x 8000)
+  bars (BASELINE.json north_star): integer histograms bit-exact for all 6 descriptor sets; all 4 cost matrices
+  within 1e-5 relative on EVERY entry; the assignment optimal for the matrix it was given (equal cost and
+  identical assignment vs the oracle on the same float32 matrix) and equal in cost to the float64 optimum;
+  same winner and inlier counts; final 4x4 within 1e-4.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    torch.cuda.set_device(0)
+    return torch
+
+
+def _stagewise(O, torch, p, trials):
+    import os
+    import platymatch_b200 as pm
+    from platymatch_b200.estimate_transform.shape_context import get_unary_counts
+    O.set_num_threads(len(os.sched_getaffinity(0)))
+    m, f = p["moving"], p["fixed"]
+    n1, n2 = m.shape[1], f.shape[1]
+    idx = [O.ransac_sample_indices(n1, 4, trials, seed=q) for q in range(4)]
+    res = pm.estimate_transform_unsupervised(m, f, ransac_trials=trials, sample_indices=idx, keep_cost=True)
+
+    # ---- descriptors: all 6 sets of the reference (2 moving + 4 fixed), integer histograms bit for bit
+    mc, fc = O.get_centroid(m, False), O.get_centroid(f, False)
+    md, fd = O.get_mean_distance(m, False), O.get_mean_distance(f, False)
+    hist = {}
+    for name, cloud, c, d, typ, nv in (("m", m, mc, md, "moving", 2), ("f", f, fc, fd, "fixed", 4)):
+        counts, dropped, ties, x0 = get_unary_counts(c, d, cloud, typ)
+        xo = O.pca_first_axis(cloud.T)
+        assert np.allclose(x0, xo, atol=1e-10)
+        for v in range(nv):
+            oc, od = O.shape_context_counts(cloud.T, c, d, xo, v + 1)
+            assert np.array_equal(counts[v], oc), (name, v)
+            assert np.array_equal(dropped[v], od), (name, v)
+            hist[name, v + 1] = O.normalise_counts(oc)
+        assert ties == 0
+
+    # ---- per hypothesis: cost matrix (every entry), assignment, RANSAC
+    inliers_o, a_o, ndiff = [], [], []
+    for q, (a, b) in enumerate(O.HYPOTHESES[:4]):
+        U = O.unary_distance_matrix(hist["m", a], hist["f", b])                 # float64, the reference's values
+        G = res["cost"][q][:, :n2]
+        nz = U > 0
+        rel = float((np.abs(G - U)[nz] / U[nz]).max())
+        assert rel < 1e-5, (q, rel)
+        assert np.all(G[~nz] == 0.0)
+        # optimal for the matrix the kernel was given: same cost AND same assignment as the oracle on it
+        G64 = G.astype(np.float64)
+        rg, cg = O.linear_sum_assignment(G64)
+        got = res["assignments"][q][1]
+        assert res["lap_cost"][q] == pytest.approx(G64[rg, cg].sum(), rel=1e-12), q
+        assert np.array_equal(got, cg), (q, int((got != cg).sum()))
+        # against the reference's float64 matrix: equal optimal cost to the cost bar; the assignment may move only
+        # where float32 rounding reorders near-ties
+        ro, co = O.linear_sum_assignment(U)
+        assert U[np.arange(n1), got].sum() == pytest.approx(U[ro, co].sum(), rel=1e-6), q
+        ndiff.append(int((got != co).sum()))
+        A, inl = O.do_ransac(m[:, ro], f[:, co], 4, trials, 16, sample_indices=idx[q])
+        inliers_o.append(inl)
+        a_o.append(A)
+    inl_g = res["inliers"].tolist()
+    best_o = int(np.argmax(inliers_o))
+    assert res["best"] == best_o, (inl_g, inliers_o)
+    for q in range(4):
+        if ndiff[q] == 0:
+            assert inl_g[q] == inliers_o[q], (q, inl_g, inliers_o)
+            if inliers_o[q] > 0:
+                assert np.allclose(res["ransac_A"][q], a_o[q], rtol=1e-7, atol=1e-7), q
+        else:       # a handful of re-ordered near-ties: the same hypothesis quality
+            assert abs(inl_g[q] - inliers_o[q]) <= max(2 * ndiff[q], 0.02 * inliers_o[q]), (q, inl_g, inliers_o, ndiff)
+
+    # ---- ICP + composition: the final 4x4
+    a_icp, resid = O.perform_icp(O.apply_affine_transform(m, a_o[best_o]), f, 50, return_residuals=True)
+    final_o = a_icp @ a_o[best_o]
+    err = float(np.abs(res["transform"] - final_o).max())
+    assert err < 1e-4, (err, ndiff)
+    if ndiff[best_o] == 0:
+        assert np.allclose(res["icp_residuals"], resid, rtol=1e-6, atol=1e-9)
+    moved = O.apply_affine_transform(m, res["transform"])
+    assert np.median(np.linalg.norm(moved - f[:, p["gt_fixed_index"]], axis=0)) < 4.0
+    return dict(ndiff=ndiff, inliers=inl_g, err=err)
+
+
+def test_config1_3k_full_oracle(O, torch):
+    """BASELINE config 1 — 'synthetic 3k-nucleus embryo-like pair ..., runs on CPU reference'."""
+    from platymatch_b200.synthetic import make_pair
+    out = _stagewise(O, torch, make_pair(3000), trials=2000)
+    print("config 1:", out)
+
+
+def test_config2_8k_full_oracle(O, torch):
+    """BASELINE config 2 — the headline 8k x 8k pair, every stage against the full oracle run."""
+    from platymatch_b200.synthetic import make_pair
+    out = _stagewise(O, torch, make_pair(8000), trials=2000)
+    print("config 2:", out)
+
+
+@pytest.mark.parametrize("n", [1500, 4000])
+def test_chi2_filled_cloud_dense_histograms(O, torch, n):
+    """Late-stage-embryo variant: nuclei fill the ellipsoid, ~2x more bins populated than on a shell,
+    so the kernel's structural-zero skipping has little to skip.  Real shape-context histograms, every entry."""
+    from platymatch_b200 import device as D, pipeline as P
+    from platymatch_b200.synthetic import make_pair
+    p = make_pair(n, filled=True)
+    m, f = p["moving"], p["fixed"]
+    dm, df = P.describe_cloud(m, 1), P.describe_cloud(f, 4)
+    mc, fc = O.get_centroid(m, False), O.get_centroid(f, False)
+    md, fd = O.get_mean_distance(m, False), O.get_mean_distance(f, False)
+    om, _ = O.shape_context_counts(m.T, mc, md, O.pca_first_axis(m.T), 1)
+    assert np.array_equal(dm.counts[0].cpu().numpy().view(np.uint32), om)
+    assert (om > 0).mean() > 0.35                                   # shells: 0.25
+    for b in (1, 4):
+        of, _ = O.shape_context_counts(f.T, fc, fd, O.pca_first_axis(f.T), b)
+        assert np.array_equal(df.counts[b - 1].cpu().numpy().view(np.uint32), of)
+        U = O.unary_distance_matrix(O.normalise_counts(om), O.normalise_counts(of))
+        G = D.chi2_cost(dm.operand(1), df.operand(b))[:, :f.shape[1]].cpu().numpy()
+        assert float((np.abs(G - U) / U).max()) < 1e-5
