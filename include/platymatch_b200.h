@@ -109,6 +109,13 @@ int pm_shape_context_hist(const double *pts, int n, const double *centroid, cons
                           const double *mean_dist, const double *r_edges, int n_redges, int n_variants,
                           uint32_t *counts, uint32_t *dropped, unsigned long long *edge_ties, void *stream);
 
+/* The same for the query nuclei [row_begin, row_end) only (descriptor rows shard across GPUs):
+ * counts [n_variants][row_end - row_begin][360], dropped [n_variants][row_end - row_begin]. */
+int pm_shape_context_hist_rows(const double *pts, int n, const double *centroid, const double *x0,
+                               const double *mean_dist, const double *r_edges, int n_redges, int n_variants,
+                               int row_begin, int row_end, uint32_t *counts, uint32_t *dropped,
+                               unsigned long long *edge_ties, void *stream);
+
 /* Normalise integer histograms (shape_context.py:41) to float32, written bin-major ("transposed"):
  * out[k * ld + i] = counts[i][k] / rowsum_i, ld >= n (pad columns hold zero_sentinel), exact zeros
  * replaced by zero_sentinel (0 keeps them).  Generic helper; the cost kernel uses pm_chi2_operand. */
@@ -225,6 +232,17 @@ int pm_apply_affine(const double *pts, int n, const double *A, double *out, void
 int pm_gather_points(const double *pts, const int32_t *index, int k, double *out, void *stream);
 /* C = A @ B for 4x4 float64 (icp @ sc, _dock_widget.py:428) */
 int pm_compose(const double *A, const double *B, double *C, void *stream);
+
+/* ---- peer-memory windows (multi-GPU; the reference is single-process) ---------------------
+ * A window is a cudaMalloc allocation exported with CUDA IPC so that the chi^2 kernels of the OTHER ranks of the
+ * box store their cost-matrix rows straight into the owner's matrix over NVLink (pm_chi2_cost with the mapped
+ * address as its output pointer).  handle64: PM_PEER_HANDLE_BYTES opaque bytes to pass between processes. */
+#define PM_PEER_HANDLE_BYTES 64
+int pm_peer_alloc(size_t bytes, void **ptr);
+int pm_peer_free(void *ptr);
+int pm_peer_export(void *ptr, unsigned char *handle64);
+int pm_peer_open(const unsigned char *handle64, void **ptr);
+int pm_peer_close(void *ptr);
 
 /* ---- host-buffer entry points (numpy callers; copy in, run, copy out, synchronise) ----------------- */
 /* get_mean_distance (utils.py:58-75) */

@@ -33,6 +33,7 @@ SIGNATURES = {
     "pm_mean_distance_workspace_bytes": (_sz, [_i]),
     "pm_mean_distance": (_i, [_vp, _i, _vp, _vp, _sz, _vp]),
     "pm_shape_context_hist": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "pm_shape_context_hist_rows": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pm_normalise_hist": (_i, [_vp, _i, _vp, _i, ctypes.c_float, _vp]),
     "pm_chi2_operand": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "pm_chi2_operand_f32": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
@@ -52,6 +53,11 @@ SIGNATURES = {
     "pm_apply_affine": (_i, [_vp, _i, _vp, _vp, _vp]),
     "pm_gather_points": (_i, [_vp, _vp, _i, _vp, _vp]),
     "pm_compose": (_i, [_vp, _vp, _vp, _vp]),
+    "pm_peer_alloc": (_i, [_sz, _vp]),
+    "pm_peer_free": (_i, [_vp]),
+    "pm_peer_export": (_i, [_vp, _vp]),
+    "pm_peer_open": (_i, [_vp, _vp]),
+    "pm_peer_close": (_i, [_vp]),
     "pm_host_mean_distance": (_i, [_vp, _i, _i, _vp]),
     "pm_host_shape_context": (_i, [_vp, _i, _vp, _d, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
 }

@@ -1242,7 +1242,10 @@ static int pm_lap_raise_smem_limit_impl(const void *kernel, int smem_optin, int 
     std::lock_guard<std::mutex> g(mu);
     for (int q = 0; q < n_seen; ++q)
         if (seen_kernel[q] == kernel && seen_dev[q] == dev) return PM_OK;
-    PM_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+    cudaFuncAttributes fa;                          // the opt-in limit covers static + dynamic shared memory
+    PM_CUDA_TRY(cudaFuncGetAttributes(&fa, kernel));
+    PM_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     smem_optin - (int)fa.sharedSizeBytes));
     if (n_seen < 64) { seen_kernel[n_seen] = kernel; seen_dev[n_seen] = dev; ++n_seen; }
     return PM_OK;
 }

@@ -94,14 +94,16 @@ template <int NVAR>
 __global__ void __launch_bounds__(PM_SC_WARPS * 32)
 pm_shape_context_kernel(const double *__restrict__ pts, int n, const double *__restrict__ centroid,
                         const double *__restrict__ x0g, const double *__restrict__ mean_dist_p,
-                        const double *__restrict__ r_edges, int n_redges, uint32_t *__restrict__ counts,
-                        uint32_t *__restrict__ dropped, unsigned long long *__restrict__ edge_ties) {
+                        const double *__restrict__ r_edges, int n_redges, int row_begin, int row_end,
+                        uint32_t *__restrict__ counts, uint32_t *__restrict__ dropped,
+                        unsigned long long *__restrict__ edge_ties) {
     __shared__ uint32_t hist0[PM_SC_WARPS][PM_NBINS];            // fast-path neighbours, variant-0 bins
     __shared__ uint32_t histx[PM_SC_WARPS][NVAR][PM_NBINS];      // exact-path neighbours, per variant
     __shared__ double tile[PM_SC_TILE * 3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i = blockIdx.x * PM_SC_WARPS + warp;
-    const bool live = i < n;
+    const int i = row_begin + blockIdx.x * PM_SC_WARPS + warp;      // query nucleus; output row i - row_begin
+    const bool live = i < row_end;
+    const int n_out = row_end - row_begin;
     const double mean_dist = mean_dist_p[0];
     const double BAND = 1e-11;
     // squared ring edges in absolute units with their undecided bands
@@ -224,7 +226,7 @@ pm_shape_context_kernel(const double *__restrict__ pts, int n, const double *__r
     if (!live) return;
 #pragma unroll
     for (int v = 0; v < NVAR; ++v) {
-        uint32_t *dst = counts + ((size_t)v * n + i) * PM_NBINS;
+        uint32_t *dst = counts + ((size_t)v * n_out + (i - row_begin)) * PM_NBINS;
         // variant v of a fast-path neighbour sits in the phi-permuted bin (exactly, away from sector edges)
         for (int k = lane; k < PM_NBINS; k += 32) dst[pm_sc_variant_bin(k, v)] = hist0[warp][k];
         __syncwarp();
@@ -233,34 +235,44 @@ pm_shape_context_kernel(const double *__restrict__ pts, int n, const double *__r
         uint32_t d = drop[v];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        if (lane == 0 && dropped) dropped[(size_t)v * n + i] = d;
+        if (lane == 0 && dropped) dropped[(size_t)v * n_out + (i - row_begin)] = d;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ties += __shfl_xor_sync(0xffffffffu, ties, o);
     if (lane == 0 && edge_ties && ties) atomicAdd(edge_ties, (unsigned long long)ties);
 }
 
-extern "C" int pm_shape_context_hist(const double *pts, int n, const double *centroid, const double *x0,
-                                     const double *mean_dist, const double *r_edges, int n_redges,
-                                     int n_variants, uint32_t *counts, uint32_t *dropped,
-                                     unsigned long long *edge_ties, void *stream) {
+extern "C" int pm_shape_context_hist_rows(const double *pts, int n, const double *centroid, const double *x0,
+                                          const double *mean_dist, const double *r_edges, int n_redges,
+                                          int n_variants, int row_begin, int row_end, uint32_t *counts,
+                                          uint32_t *dropped, unsigned long long *edge_ties, void *stream) {
     PM_REQUIRE(pts && centroid && x0 && mean_dist && r_edges && counts, "null pointer");
     PM_REQUIRE(n >= 2, "need at least 2 points");
     PM_REQUIRE(n_redges >= 1 && n_redges <= 5, "n_redges must be 1..5 (5 rings x 72 = 360 bins)");
     PM_REQUIRE(n_variants == 1 || n_variants == 2 || n_variants == 4, "n_variants must be 1, 2 or 4");
-    const int blocks = (n + PM_SC_WARPS - 1) / PM_SC_WARPS;
+    PM_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= n, "need 0 <= row_begin <= row_end <= n");
+    if (row_end == row_begin) return PM_OK;
+    const int blocks = (row_end - row_begin + PM_SC_WARPS - 1) / PM_SC_WARPS;
     cudaStream_t s = pm_stream(stream);
     if (n_variants == 1)
         pm_shape_context_kernel<1><<<blocks, PM_SC_WARPS * 32, 0, s>>>(pts, n, centroid, x0, mean_dist, r_edges,
-                                                                     n_redges, counts, dropped, edge_ties);
+                                                                     n_redges, row_begin, row_end, counts, dropped, edge_ties);
     else if (n_variants == 2)
         pm_shape_context_kernel<2><<<blocks, PM_SC_WARPS * 32, 0, s>>>(pts, n, centroid, x0, mean_dist, r_edges,
-                                                                     n_redges, counts, dropped, edge_ties);
+                                                                     n_redges, row_begin, row_end, counts, dropped, edge_ties);
     else
         pm_shape_context_kernel<4><<<blocks, PM_SC_WARPS * 32, 0, s>>>(pts, n, centroid, x0, mean_dist, r_edges,
-                                                                     n_redges, counts, dropped, edge_ties);
+                                                                     n_redges, row_begin, row_end, counts, dropped, edge_ties);
     PM_LAUNCH_CHECK();
     return PM_OK;
+}
+
+extern "C" int pm_shape_context_hist(const double *pts, int n, const double *centroid, const double *x0,
+                                     const double *mean_dist, const double *r_edges, int n_redges,
+                                     int n_variants, uint32_t *counts, uint32_t *dropped,
+                                     unsigned long long *edge_ties, void *stream) {
+    return pm_shape_context_hist_rows(pts, n, centroid, x0, mean_dist, r_edges, n_redges, n_variants, 0, n, counts,
+                                      dropped, edge_ties, stream);
 }
 
 // Normalise to float32, bin-major (coalesced operand layout of the chi^2 kernel).

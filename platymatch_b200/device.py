@@ -33,8 +33,11 @@ def to_device_points(cloud, transposed=False, device=None):
         return t[:, :3].contiguous().to(device or "cuda")
     a = np.asarray(cloud, dtype=np.float64)
     a = a if transposed else a.T
-    a = np.ascontiguousarray(a[:, :3])
-    return torch.from_numpy(a).to(device or "cuda", non_blocking=True)
+    # the layout change (3xN -> [N,3]) lands directly in PINNED host memory, so the host -> device copy is one
+    # asynchronous DMA (torch's pinned-block cache keeps the block alive until the copy has completed)
+    staged = torch.empty((a.shape[0], 3), dtype=torch.float64, pin_memory=True)
+    staged.numpy()[...] = a[:, :3]
+    return staged.to(device or "cuda", non_blocking=True)
 
 
 def cloud_stats(pts):
@@ -56,18 +59,20 @@ def mean_distance(pts):
     return out
 
 
-def shape_context_counts(pts, centroid, x0, mean_dist, n_variants, r_edges=None):
-    """Integer histograms [n_variants, N, 360] uint32 (as int32 tensor), dropped [n_variants, N], ties [1]."""
+def shape_context_counts(pts, centroid, x0, mean_dist, n_variants, r_edges=None, rows=None):
+    """Integer histograms [n_variants, N, 360] uint32 (as int32 tensor), dropped [n_variants, N], ties [1].
+    rows = (begin, end): only those query nuclei -> [n_variants, end - begin, 360] (descriptor rows shard across GPUs)."""
     torch = _torch()
     n = pts.shape[0]
+    begin, end = (0, n) if rows is None else rows
     if r_edges is None:
         r_edges = torch.from_numpy(R_EDGES).to(pts.device)
-    counts = torch.empty((n_variants, n, NBINS), dtype=torch.int32, device=pts.device)
-    dropped = torch.empty((n_variants, n), dtype=torch.int32, device=pts.device)
+    counts = torch.empty((n_variants, end - begin, NBINS), dtype=torch.int32, device=pts.device)
+    dropped = torch.empty((n_variants, end - begin), dtype=torch.int32, device=pts.device)
     ties = torch.zeros(1, dtype=torch.int64, device=pts.device)
-    check(load().pm_shape_context_hist(ptr(pts), n, ptr(centroid), ptr(x0), ptr(mean_dist), ptr(r_edges),
-                                       r_edges.numel(), n_variants, ptr(counts), ptr(dropped), ptr(ties),
-                                       stream_ptr()), "pm_shape_context_hist")
+    check(load().pm_shape_context_hist_rows(ptr(pts), n, ptr(centroid), ptr(x0), ptr(mean_dist), ptr(r_edges),
+                                            r_edges.numel(), n_variants, begin, end, ptr(counts), ptr(dropped),
+                                            ptr(ties), stream_ptr()), "pm_shape_context_hist_rows")
     return counts, dropped, ties
 
 
@@ -110,12 +115,20 @@ def chi2_operand(hist_2d):
     return Chi2Operand(out, mask, n)
 
 
-def chi2_cost(a, b, out=None, row_begin=0, row_end=None):
-    """cost[row_begin:row_end, :b.n] float32 (ld = b.n rounded up to 4) for two Chi2Operands (rows a, columns b)."""
+def chi2_cost(a, b, out=None, row_begin=0, row_end=None, out_ptr=None, out_ld=None):
+    """cost[row_begin:row_end, :b.n] float32 (ld = b.n rounded up to 4) for two Chi2Operands (rows a, columns b).
+    out_ptr / out_ld: raw device address of the first output row and its leading dimension instead of a tensor -
+    a peer-mapped window of another rank (PeerWindow): the kernel's stores go over NVLink."""
     torch = _torch()
     n1, n2 = a.n, b.n
     row_end = n1 if row_end is None else row_end
     ldc = (n2 + 3) // 4 * 4
+    if out_ptr is not None:
+        import ctypes
+        check(load().pm_chi2_cost(ptr(a.t), a.ld, ptr(a.mask), n1, ptr(b.t), b.ld, ptr(b.mask), n2, row_begin, row_end,
+                                  ctypes.c_void_p(int(out_ptr)), int(out_ld if out_ld is not None else ldc), stream_ptr()),
+              "pm_chi2_cost")
+        return None
     if out is None:
         out = torch.empty((row_end - row_begin, ldc), dtype=torch.float32, device=a.t.device)
     assert out.stride(-1) == 1 and out.shape[-1] >= n2
@@ -282,3 +295,58 @@ def cdist(a, b):
     out = torch.zeros((n1, ld), dtype=torch.float32, device=a.device)
     check(load().pm_cdist(ptr(a), n1, ptr(b), n2, ptr(out), ld, stream_ptr()), "pm_cdist")
     return out
+
+
+class PeerWindow:
+    """A per-rank device buffer that every rank of the box can store into (CUDA IPC over NVLink; pm_peer.cu).
+    `local` is this rank's buffer as a uint8 torch tensor view; `remote[r]` is the address at which rank r's buffer
+    is mapped in this process (remote[rank] = the local address).  Collective: every rank of `group` constructs it
+    with the same `nbytes`."""
+
+    def __init__(self, nbytes, group=None):
+        import ctypes
+        import torch.distributed as dist
+        torch = _torch()
+        self.nbytes, self.group = int(nbytes), group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        p = ctypes.c_void_p()
+        check(load().pm_peer_alloc(self.nbytes, ctypes.byref(p)), "pm_peer_alloc")
+        self.ptr = p.value
+        handle = (ctypes.c_ubyte * 64)()
+        check(load().pm_peer_export(ctypes.c_void_p(self.ptr), handle), "pm_peer_export")
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+        everyone = torch.empty((self.world, 64), dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(everyone, mine, group=group)
+        handles = everyone.cpu().numpy()
+        self.remote, self._opened = [], []
+        for r in range(self.world):
+            if r == self.rank:
+                self.remote.append(self.ptr)
+                continue
+            q = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64)(*handles[r].tolist())
+            check(load().pm_peer_open(buf, ctypes.byref(q)), "pm_peer_open")
+            self.remote.append(q.value)
+            self._opened.append(q.value)
+
+    def tensor(self, shape, dtype, offset_bytes=0):
+        """A torch view of (part of) the local buffer."""
+        torch = _torch()
+        n = int(np.prod(shape))
+        itemsize = torch.empty(0, dtype=dtype).element_size()
+        assert offset_bytes + n * itemsize <= self.nbytes
+        iface = {"shape": tuple(int(x) for x in shape), "typestr": np.dtype(str(dtype).replace("torch.", "")).str,
+                 "data": (self.ptr + offset_bytes, False), "version": 2}
+        holder = type("_Win", (), {"__cuda_array_interface__": iface})()
+        return torch.as_tensor(holder, device="cuda")
+
+    def close(self):
+        import ctypes
+        torch = _torch()
+        torch.cuda.synchronize()
+        for q in self._opened:
+            load().pm_peer_close(ctypes.c_void_p(q))
+        self._opened = []
+        if self.ptr:
+            load().pm_peer_free(ctypes.c_void_p(self.ptr))
+            self.ptr = None

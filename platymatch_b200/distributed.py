@@ -1,25 +1,34 @@
 """Multi-GPU sharding of the registration path: one process per GPU,
-`torch.distributed` (NCCL over NVLink on the GPU box, gloo in the CPU tests) for the two real
-exchange steps, nothing else.
+`torch.distributed` (NCCL over NVLink on the GPU box, gloo in the CPU tests) for the plumbing.
 
-Three ways the path shards, all with static partitions:
+Three ways the path shards:
 
-  * specimen pairs      independent registrations -> round-robin over ranks, no data-path collective;
-                        one all_gather of the 4x4 results at the end (`register_all_pairs`).
-  * hypotheses          the H {cost matrix -> LAP -> RANSAC} chains are independent -> hypothesis q
-                        runs on rank q % world; one all_gather of (inliers, 4x4) picks the winner
-                        (`reduce_best_hypothesis`), every rank then refines with ICP (replicated,
-                        deterministic) so all ranks return the same transform.
-  * cost-matrix rows    for large clouds the rows of every cost matrix are computed in row shards
-                        (`shard_rows`) and exchanged with one all_gather per matrix (`allgather_rows`)
-                        so that the LAP owner holds the full matrix.  The LAP itself does not shard
-                        across GPUs ("replicas only"): one matrix, one GPU.
+  * specimen pairs      independent registrations (config 5: 12 specimens, 66 pairs).  Descriptors of the
+                        specimens are computed once, spread over the ranks, and all-gathered; the pairs are then
+                        pulled from ONE shared work counter (a fetch-add on the job's rendezvous store) by every
+                        in-flight worker of every rank, so neither the 66 / 8 remainder nor the 8-20 ms spread of
+                        the assignment stage leaves a rank idle.  No data-path collective; one all-reduce of the
+                        4x4 results at the end (`register_all_pairs`).
+  * hypotheses          the H {cost matrix -> LAP -> RANSAC} chains are independent -> hypothesis q is owned by
+                        rank `owner_of_hypothesis(q)`; one all-gather of (inliers, 4x4) picks the winner
+                        (`reduce_best_hypothesis`), every rank then refines with ICP (replicated, deterministic)
+                        so all ranks return the same transform.
+  * rows                for large clouds (config 4, 20k x 20k) the query rows of the descriptor kernel and the
+                        rows of every cost matrix are split over ALL ranks.  Descriptor rows come back with one
+                        all-gather (`allgather_counts`); cost rows are delivered to the matrix OWNER ONLY: on NCCL
+                        the chi^2 kernel stores them straight into the owner's matrix through a peer-mapped window
+                        (device.PeerWindow, CUDA IPC over NVLink: compute and transfer are one kernel), otherwise
+                        (gloo, or PM_DIST_NO_PEER=1) with one `dist.gather` per matrix (`gather_rows_to_owner`).
+                        The LAP itself does not shard across GPUs ("replicas only"): one matrix, one GPU.
 
-The partition arithmetic and both exchange steps are plain-tensor code (CPU or CUDA), covered by
-world_size-2 gloo tests in tests/test_distributed_cpu.py; only `register_pair_sharded` and
-`register_all_pairs` touch the CUDA library.
+The partition arithmetic and the exchange steps are plain-tensor code (CPU or CUDA), covered by world_size-2
+gloo tests in tests/test_distributed_cpu.py; `register_pair_sharded` and `register_all_pairs` touch the CUDA
+library and are covered by tests/test_gpu_distributed.py (torchrun, NCCL, 2 GPUs).
 """
 import itertools
+import os
+import threading
+import time
 
 import numpy as np
 
@@ -42,9 +51,16 @@ def shard_rows(n_rows, rank, world, align=128):
     return begin, end, per
 
 
+def owner_of_hypothesis(q, n_hyp, world):
+    """Rank that solves hypothesis q's assignment: owners are spread evenly over the ranks (4 hypotheses on 8 GPUs
+    -> ranks 0, 2, 4, 6), round-robin when there are more hypotheses than ranks."""
+    if world >= n_hyp:
+        return q * (world // n_hyp)
+    return q % world
+
+
 def hypotheses_for_rank(n_hyp, rank, world):
-    """Hypothesis q is owned by rank q % world."""
-    return [q for q in range(n_hyp) if q % world == rank]
+    return [q for q in range(n_hyp) if owner_of_hypothesis(q, n_hyp, world) == rank]
 
 
 def all_pairs(n_specimens):
@@ -53,14 +69,78 @@ def all_pairs(n_specimens):
 
 
 def pairs_for_rank(n_specimens, rank, world):
-    """Static round-robin of the pair list: pair p goes to rank p % world."""
+    """Static round-robin of the pair list (pair p -> rank p % world): the schedule `register_all_pairs` falls back
+    to without a work counter (`dynamic=False`)."""
     return [p for k, p in enumerate(all_pairs(n_specimens)) if k % world == rank]
 
 
+class WorkCounter:
+    """Shared fetch-add counter for dynamic scheduling across ranks: `next()` returns 0, 1, 2, ... exactly once over
+    all callers (threads and ranks).  Backed by the process group's rendezvous store (an atomic `add` on the TCP
+    store: ~0.1 ms per item, against ~19 ms of GPU work per registration)."""
+    _serial = 0
+
+    def __init__(self, group=None):
+        self._local = itertools.count()
+        self._lock = threading.Lock()
+        self._store = None
+        rank, world = world_info(group)
+        if world > 1:
+            from torch.distributed.distributed_c10d import _get_default_store
+            self._store = _get_default_store()
+            # the same key on every rank, a fresh one per counter: counters are created collectively, in the same order
+            WorkCounter._serial += 1
+            self._key = "platymatch_b200/work/%d" % WorkCounter._serial
+
+    def next(self):
+        if self._store is None:
+            with self._lock:
+                return next(self._local)
+        return int(self._store.add(self._key, 1)) - 1
+
+
 # ----------------------------------------------------------------------------- exchange steps
+def _raise_together(error, group=None):
+    """All ranks learn whether ANY rank failed before the next collective, and raise together: a rank that raised
+    alone would leave the others blocked in that collective for ever."""
+    import torch
+    import torch.distributed as dist
+    rank, world = world_info(group)
+    if world > 1:
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        flag = torch.tensor([1 if error is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        failed = int(flag.item()) != 0
+    else:
+        failed = error is not None
+    if error is not None:
+        raise error
+    if failed:
+        raise RuntimeError("platymatch_b200: another rank failed in this collective step (see its traceback)")
+
+
+def gather_rows_to_owner(local_rows, n_rows, per, owner, group=None):
+    """Row shards -> the owner only.  local_rows is this rank's [per, ld] block (rows beyond the rank's range are
+    padding); returns the full [n_rows, ld] matrix on `owner`, None elsewhere.  (1 / world of the bytes and of the
+    memory of an all-gather: only the rank that solves the matrix needs it.)"""
+    import torch
+    import torch.distributed as dist
+    rank, world = world_info(group)
+    if world == 1:
+        return local_rows[:n_rows]
+    assert local_rows.shape[0] == per
+    local_rows = local_rows.contiguous()
+    if rank == owner:
+        parts = [torch.empty_like(local_rows) for _ in range(world)]
+        dist.gather(local_rows, parts, dst=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+        return torch.cat(parts, 0)[:n_rows]
+    dist.gather(local_rows, None, dst=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+    return None
+
+
 def allgather_rows(local_rows, n_rows, per, group=None):
-    """All-gather of row shards: local_rows is this rank's [per, ld] block (rows beyond the rank's range
-    are padding); returns the full [n_rows, ld] matrix on every rank."""
+    """All-gather of row shards (used for the descriptor histograms, which every rank needs): local_rows is this
+    rank's [per, ...] block; returns the full [n_rows, ...] array on every rank."""
     import torch
     import torch.distributed as dist
     rank, world = world_info(group)
@@ -80,7 +160,7 @@ def reduce_best_hypothesis(inliers_local, transforms_local, hyp_ids_local, n_hyp
     import torch.distributed as dist
     rank, world = world_info(group)
     dev = transforms_local.device
-    slots = -(-n_hyp // world)
+    slots = max(1, -(-n_hyp // world))
     pack = torch.full((slots, 18), -1.0, dtype=torch.float64, device=dev)
     for k, q in enumerate(hyp_ids_local):
         pack[k, 0] = float(q)
@@ -121,88 +201,242 @@ def gather_results(local, n_total, owner_of, group=None):
 
 
 # ----------------------------------------------------------------------------- CUDA paths
-def register_pair_sharded(moving, fixed, *, ransac_samples=4, ransac_trials=8000, ransac_error=16, icp_iterations=50,
-                          seed=0, hypotheses=None, max_bid_rounds=2048, shard_rows_of_cost=True, group=None):
-    """One registration spread over all ranks (configs 2/4 at N > 1): cost-matrix rows of every hypothesis are
-    computed in row shards and all-gathered to all ranks; hypothesis q's LAP + RANSAC run on rank q % world;
-    (inliers, A) are all-gathered; every rank runs the (deterministic) ICP.  Returns the same dict on every rank."""
+def describe_cloud_sharded(cloud, n_variants, group=None, transposed=False):
+    """pipeline.describe_cloud with the query rows of the shape-context kernel (the O(N^2) part) split over the
+    ranks and the integer histograms all-gathered.  Centroid / PCA axis / mean distance are replicated (cheap and
+    deterministic, so every rank bins against bit-identical frames).  Returns the same Descriptors on every rank."""
     import torch
+    from . import device as D, pipeline as P
+    rank, world = world_info(group)
+    if world == 1:
+        return P.describe_cloud(cloud, n_variants, transposed)
+    pts = cloud if (torch.is_tensor(cloud) and cloud.is_cuda and transposed) else D.to_device_points(cloud, transposed=transposed)
+    n = pts.shape[0]
+    stats = D.cloud_stats(pts)
+    md = D.mean_distance(pts)
+    begin, end, per = shard_rows(n, rank, world, align=8)
+    local = torch.zeros((per, n_variants, D.NBINS + 1), dtype=torch.int32, device=pts.device)   # [..., 360] = dropped
+    ties = torch.zeros(1, dtype=torch.int64, device=pts.device)
+    if end > begin:
+        counts, dropped, ties = D.shape_context_counts(pts, stats[0:3], stats[3:6], md, n_variants, rows=(begin, end))
+        local[:end - begin, :, :D.NBINS] = counts.permute(1, 0, 2)
+        local[:end - begin, :, D.NBINS] = dropped.permute(1, 0)
+    full = allgather_rows(local, n, per, group)                      # [n, V, 361]
+    counts = full[:, :, :D.NBINS].permute(1, 0, 2).contiguous()
+    dropped = full[:, :, D.NBINS].permute(1, 0).contiguous()
+    import torch.distributed as dist
+    dist.all_reduce(ties, group=group)
+    return P.Descriptors(pts, stats, md, counts, dropped, ties)
+
+
+_WINDOWS = {}
+
+
+def _cost_window(nbytes, group=None):
+    """This rank's peer-mapped cost-matrix window (grown on demand, reused across registrations).  Collective."""
+    from . import device as D
+    key = id(group)
+    win = _WINDOWS.get(key)
+    if win is None or win.nbytes < nbytes:
+        if win is not None:
+            win.close()
+        win = _WINDOWS[key] = D.PeerWindow(nbytes, group)
+    return win
+
+
+def close_windows():
+    for win in _WINDOWS.values():
+        win.close()
+    _WINDOWS.clear()
+
+
+def register_pair_sharded(moving, fixed, *, ransac_samples=4, ransac_trials=8000, ransac_error=16, icp_iterations=50,
+                          seed=0, hypotheses=None, max_bid_rounds=2048, transform='Affine', peer_stores=None,
+                          group=None, timings=None):
+    """One registration spread over all ranks (config 4, 20k x 20k).
+
+    descriptor rows   split over the ranks, histograms all-gathered (describe_cloud_sharded);
+    cost rows         rank r computes rows [r * per, (r + 1) * per) of EVERY hypothesis' matrix and delivers them to
+                      that matrix' owner only — through the owner's peer-mapped window (the kernel's own stores, NCCL)
+                      or one gather per matrix;
+    LAP + RANSAC      on the owner of each hypothesis; (inliers, A) all-gathered; first maximum wins;
+    ICP               replicated on every rank (deterministic).
+    Returns the same dict of numpy results on every rank.  timings: optional dict that receives the host-clock
+    duration of the stages of THIS rank (synchronising; for benchmarks only)."""
+    import torch
+    import torch.distributed as dist
     from . import device as D, pipeline as P
     rank, world = world_info(group)
     hyps = P.HYPOTHESES_DISTINCT if hypotheses is None else list(hypotheses)
     H = len(hyps)
     need_m, need_f = max(a for a, _ in hyps), max(b for _, b in hyps)
-    dm = P.describe_cloud(moving, 1 if need_m == 1 else 2)
-    df = P.describe_cloud(fixed, 1 if need_f == 1 else (2 if need_f == 2 else 4))
+    nccl = world > 1 and dist.get_backend(group) == "nccl"
+    if peer_stores is None:
+        peer_stores = nccl and not os.environ.get("PM_DIST_NO_PEER")
+
+    def mark(name, t0):
+        if timings is not None:
+            torch.cuda.synchronize()
+            timings[name] = timings.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return time.perf_counter()
+
+    t0 = time.perf_counter()
+    dm = describe_cloud_sharded(moving, 1 if need_m == 1 else 2, group)
+    df = describe_cloud_sharded(fixed, 1 if need_f == 1 else (2 if need_f == 2 else 4), group)
     n1, n2 = dm.n, df.n
-    assert n1 <= n2, "sharded path expects n_moving <= n_fixed (swap the clouds otherwise)"
+    if n1 > n2:
+        raise ValueError("sharded path expects n_moving <= n_fixed (swap the clouds otherwise)")
+    for a, _ in hyps:
+        dm.operand(a)
+    for _, b in hyps:
+        df.operand(b)
+    t0 = mark("describe", t0)
     ldc = (n2 + 3) // 4 * 4
     mine = hypotheses_for_rank(H, rank, world)
     begin, end, per = shard_rows(n1, rank, world)
+    dev = dm.pts.device
     costs = {}
-    for q, (a, b) in enumerate(hyps):
-        if world > 1 and shard_rows_of_cost:
-            local = torch.zeros((per, ldc), dtype=torch.float32, device=dm.pts.device)
+    exchanged = 0
+    if world == 1:
+        for q, (a, b) in enumerate(hyps):
+            costs[q] = D.chi2_cost(dm.operand(a), df.operand(b))
+    elif peer_stores:
+        slots = max(1, -(-H // world))
+        win = _cost_window(slots * n1 * ldc * 4, group)             # collective (first call / growth only)
+        for q in mine:
+            costs[q] = win.tensor((n1, ldc), torch.float32, offset_bytes=mine.index(q) * n1 * ldc * 4)
+        dist.barrier(group)                                          # the owners' previous matrices are no longer in use
+        order = [(q + rank) % H for q in range(H)]                   # spread the inbound traffic over the owners
+        for q in order:
+            a, b = hyps[q]
+            own = owner_of_hypothesis(q, H, world)
+            slot = hypotheses_for_rank(H, own, world).index(q)
+            if end > begin:
+                D.chi2_cost(dm.operand(a), df.operand(b), row_begin=begin, row_end=end, out_ld=ldc,
+                            out_ptr=win.remote[own] + (slot * n1 + begin) * ldc * 4)
+                if own != rank:
+                    exchanged += (end - begin) * ldc * 4
+        # stream-ordered barrier: when it completes here, every rank's kernels (and with them their peer stores) have
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, group=group)
+    else:
+        for q, (a, b) in enumerate(hyps):
+            local = torch.zeros((per, ldc), dtype=torch.float32, device=dev)
             if end > begin:
                 D.chi2_cost(dm.operand(a), df.operand(b), out=local, row_begin=begin, row_end=end)
-            full = allgather_rows(local, n1, per, group)
-            if q in mine:
+            own = owner_of_hypothesis(q, H, world)
+            full = gather_rows_to_owner(local, n1, per, own, group)
+            if own == rank:
                 costs[q] = full.contiguous()
-        elif q in mine:
-            costs[q] = D.chi2_cost(dm.operand(a), df.operand(b))
-    inl_local, a_local, lap_cost = [], [], {}
-    rows = torch.arange(n1, dtype=torch.int32, device=dm.pts.device)
-    for q in mine:
-        col4row, total, _ = D.lap_solve(costs[q], n1, n2, max_bid_rounds)
-        mk = D.gather_points(dm.pts, rows)
-        fk = D.gather_points(df.pts, col4row[0].contiguous())
-        a, inl, _, _ = D.ransac_affine(mk, fk, int(ransac_trials), float(ransac_error), int(ransac_samples), None,
-                                       seed=(int(seed) << 8) + q)
-        inl_local.append(inl[0]); a_local.append(a); lap_cost[q] = float(total.item())
-    a_stack = torch.stack(a_local) if a_local else torch.empty((0, 16), dtype=torch.float64, device=dm.pts.device)
-    inliers, transforms, best = reduce_best_hypothesis(inl_local, a_stack, mine, H, group)
+            else:
+                exchanged += (end - begin) * ldc * 4
+    t0 = mark("chi2_cost+exchange", t0)
+    a_local = torch.empty((len(mine), 16), dtype=torch.float64, device=dev)
+    inl_local = torch.empty(max(len(mine), 1), dtype=torch.int32, device=dev)
+    lap_cost, error = {}, None
+    try:
+        for k, q in enumerate(mine):
+            col4row, total, _ = D.lap_solve(costs[q], n1, n2, max_bid_rounds)
+            fk = D.gather_points(df.pts, col4row[0])
+            D.ransac(dm.pts, fk, int(ransac_trials), float(ransac_error), int(ransac_samples), None,
+                     seed=(int(seed) << 8) + q, transform=transform, out=(a_local[k], inl_local[k:k + 1]))
+            lap_cost[q] = total
+    except Exception as e:          # raised on all ranks together, below
+        error = e
+    _raise_together(error, group)
+    t0 = mark("lap+ransac", t0)
+    inliers, transforms, best = reduce_best_hypothesis(inl_local, a_local, mine, H, group)
     a_sc = transforms[best].contiguous()
     moved = D.apply_affine(dm.pts, a_sc)
-    a_icp, resid, _ = D.icp_affine(moved, df.pts, int(icp_iterations))
+    a_icp, resid, _ = D.icp(moved, df.pts, int(icp_iterations), transform=transform)
     a_final = D.compose(a_icp, a_sc)
-    return dict(transform=a_final.cpu().numpy().reshape(4, 4), transform_sc=a_sc.cpu().numpy().reshape(4, 4),
-                transform_icp=a_icp.cpu().numpy().reshape(4, 4), inliers=inliers.cpu().numpy(), best=best,
-                lap_cost=lap_cost, icp_residuals=resid.cpu().numpy())
+    out = dict(transform=a_final.cpu().numpy().reshape(4, 4), transform_sc=a_sc.cpu().numpy().reshape(4, 4),
+               transform_icp=a_icp.cpu().numpy().reshape(4, 4), inliers=inliers.cpu().numpy(), best=best,
+               lap_cost={q: float(v.item()) for q, v in lap_cost.items()}, icp_residuals=resid.cpu().numpy(),
+               exchanged_bytes=exchanged, peer_stores=bool(peer_stores and world > 1))
+    mark("reduce+icp", t0)
+    return out
 
 
-def register_all_pairs(specimens, *, group=None, in_flight=3, **kw):
-    """Batched all-pairs registration (config 5): descriptors of each specimen are computed once per rank
-    that needs them, pairs are sharded round-robin over the ranks, the 4x4 results are gathered on every rank.
+def describe_specimens(specimens, n_variants=4, group=None):
+    """Descriptors of every specimen on every rank: specimen s is described by rank s % world, the integer
+    histograms are all-gathered (config 5: 12 x 8000 x 360 x 4 variants = 553 MB over NVLink instead of 12 x the
+    O(N^2) kernel on every rank)."""
+    import torch
+    import torch.distributed as dist
+    from . import device as D, pipeline as P
+    rank, world = world_info(group)
+    if world == 1:
+        return [P.describe_cloud(s, n_variants) for s in specimens]
+    pts = [D.to_device_points(s) for s in specimens]
+    out = []
+    rounds = -(-len(specimens) // world)
+    for r in range(rounds):
+        batch = list(range(r * world, min((r + 1) * world, len(specimens))))
+        n_max = max(pts[s].shape[0] for s in batch)
+        local = torch.zeros((n_max, n_variants, D.NBINS + 1), dtype=torch.int32, device="cuda")
+        small = torch.zeros(18, dtype=torch.float64, device="cuda")            # stats[16], mean distance, edge ties
+        s = r * world + rank
+        if s < len(specimens):
+            d = P.describe_cloud(pts[s], n_variants, transposed=True)
+            local[:d.n, :, :D.NBINS] = d.counts.permute(1, 0, 2)
+            local[:d.n, :, D.NBINS] = d.dropped.permute(1, 0)
+            small[:16], small[16], small[17] = d.stats, d.mean_dist[0], d.ties[0].to(torch.float64)
+        full = torch.empty((world,) + tuple(local.shape), dtype=torch.int32, device="cuda")
+        smalls = torch.empty((world, 18), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(full, local, group=group)
+        dist.all_gather_into_tensor(smalls, small, group=group)
+        for k, s in enumerate(batch):
+            n = pts[s].shape[0]
+            counts = full[k, :n, :, :D.NBINS].permute(1, 0, 2).contiguous()
+            dropped = full[k, :n, :, D.NBINS].permute(1, 0).contiguous()
+            out.append(P.Descriptors(pts[s], smalls[k, :16].clone(), smalls[k, 16:17].clone(), counts, dropped,
+                                     smalls[k, 17:18].to(torch.int64)))
+    return out
+
+
+def register_all_pairs(specimens, *, group=None, in_flight=3, dynamic=True, stats=None, **kw):
+    """Batched all-pairs registration (config 5): descriptors of each specimen are computed once (spread over the
+    ranks, all-gathered), the pairs are pulled from one shared work counter by every in-flight worker of every rank
+    (`dynamic=False`: static round-robin), the 4x4 results are gathered on every rank.
     On each rank `in_flight` independent registrations overlap on separate CUDA streams (one host thread each):
     the assignment stage is latency-bound on a few SMs and hides behind the cost-matrix / ICP kernels of the
-    other pairs.  specimens: list of 3xN arrays.  Returns (pairs, transforms[n_pairs,4,4])."""
-    import threading
+    other pairs.  specimens: list of 3xN arrays.  Returns (pairs, transforms[n_pairs,4,4]).
+    stats: optional dict receiving this rank's pair count and busy time."""
     import torch
     from . import pipeline as P
     rank, world = world_info(group)
     pairs = all_pairs(len(specimens))
-    mine = [(k, p) for k, p in enumerate(pairs) if k % world == rank]
-    desc = {}
-    for _, (i, j) in mine:       # variants 1-2 double as the 'moving' sets
-        for s in (i, j):
-            if s not in desc:
-                desc[s] = P.describe_cloud(specimens[s], 4)
-    for d in desc.values():      # operands are built lazily: do it here, before the streams fork
+    desc = describe_specimens(specimens, 4, group)
+    for d in desc:               # operands are built lazily: do it here, before the streams fork
         for v in (1, 2, 3, 4):
             d.operand(v)
     torch.cuda.synchronize()
-    local, errors = {}, []
-    nfl = max(1, min(int(in_flight), len(mine)))
+    counter = WorkCounter(group) if dynamic else None
+    static = [k for k in range(len(pairs)) if k % world == rank]
+    local, errors, done = {}, [], []
+    nfl = max(1, int(in_flight))
     dev = torch.cuda.current_device()
+    t_begin = time.perf_counter()
 
     def worker(w):
         try:
             torch.cuda.set_device(dev)
             with torch.cuda.stream(torch.cuda.Stream()):
-                for k, (i, j) in mine[w::nfl]:      # moving = specimen i, fixed = specimen j (tall problems are transposed inside)
+                mine = iter(static[w::nfl])
+                results = []
+                while True:
+                    k = counter.next() if dynamic else next(mine, len(pairs))
+                    if k >= len(pairs):
+                        break
+                    i, j = pairs[k]     # moving = specimen i, fixed = specimen j (tall problems are transposed inside)
                     res = P.register_described(desc[i], desc[j], seed=k, overlap_hypotheses=(nfl == 1), **kw)
-                    local[k] = res["transform"].cpu().numpy().reshape(4, 4)
-        except Exception as e:     # surfaced below: a worker must not die silently
+                    results.append((k, res["transform"]))
+                torch.cuda.current_stream().synchronize()
+                for k, t in results:
+                    local[k] = t.cpu().numpy().reshape(4, 4)
+                done.append(len(results))
+        except Exception as e:     # surfaced below, on all ranks together: a worker must not die silently
             errors.append(e)
 
     if nfl == 1:
@@ -213,7 +447,9 @@ def register_all_pairs(specimens, *, group=None, in_flight=3, **kw):
             t.start()
         for t in ts:
             t.join()
-    if errors:
-        raise errors[0]
+    busy = time.perf_counter() - t_begin
+    _raise_together(errors[0] if errors else None, group)
+    if stats is not None:
+        stats.update(pairs_done=int(sum(done)), busy_s=busy, rank=rank)
     out = gather_results(local, len(pairs), None, group)
     return pairs, out.numpy().reshape(-1, 4, 4)

@@ -1,5 +1,6 @@
-"""Host-side logic of the multi-GPU path on CPU: partition arithmetic, and the two exchange steps
-(row all-gather, best-hypothesis reduction) over a world_size-2 gloo group."""
+"""Host-side logic of the multi-GPU path on CPU: partition arithmetic, and the exchange steps (row delivery to the
+owner only, row all-gather, best-hypothesis reduction, result gather, the shared work counter, raising together)
+over a world_size-2 gloo group."""
 import os
 import socket
 
@@ -35,6 +36,13 @@ def test_pair_and_hypothesis_partitions():
         assert sorted(seen) == pairs
         hyp = sorted(q for r in range(world) for q in PD.hypotheses_for_rank(4, r, world))
         assert hyp == [0, 1, 2, 3]
+        for n_hyp in (4, 8):
+            owners = [PD.owner_of_hypothesis(q, n_hyp, world) for q in range(n_hyp)]
+            assert all(0 <= o < world for o in owners)
+            load = [owners.count(r) for r in range(world)]
+            assert max(load) == -(-n_hyp // world)              # as even as it gets
+            assert all(q in PD.hypotheses_for_rank(n_hyp, owners[q], world) for q in range(n_hyp))
+    assert [PD.owner_of_hypothesis(q, 4, 8) for q in range(4)] == [0, 2, 4, 6]
 
 
 def _free_port():
@@ -57,6 +65,37 @@ def _worker(rank, world, port, q):
         local[: e - b] = truth[b:e]
         full = PD.allgather_rows(local, n_rows, per)
         ok_rows = bool(torch.equal(full, truth))
+        # --- row delivery to the owner only: each matrix lands on its owner, nobody else holds it
+        for owner in range(world):
+            got = PD.gather_rows_to_owner(local * (owner + 1), n_rows, per, owner)
+            ok_rows &= (got is None) if rank != owner else bool(torch.equal(got, truth * (owner + 1)))
+        # --- shared work counter: every index exactly once over all ranks and threads
+        import threading
+        counter = PD.WorkCounter()
+        taken = []
+
+        def pull():
+            while True:
+                k = counter.next()
+                if k >= 40:
+                    return
+                taken.append(k)
+        ts = [threading.Thread(target=pull) for _ in range(3)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        mine_t = torch.zeros(40, dtype=torch.int32)
+        mine_t[taken] += 1
+        dist.all_reduce(mine_t)
+        ok_rows &= bool(torch.all(mine_t == 1)) and len(set(taken)) == len(taken)
+        # --- raise together: rank 1 fails, BOTH raise (nobody is left waiting in the next collective)
+        try:
+            PD._raise_together(ValueError("boom") if rank == 1 else None)
+            ok_rows = False
+        except ValueError:
+            ok_rows &= rank == 1
+        except RuntimeError:
+            ok_rows &= rank == 0
+        PD._raise_together(None)
         # --- best-hypothesis reduction: ties resolve to the first hypothesis (np.argmax)
         inl_all = [17, 42, 42, 5]
         mine = PD.hypotheses_for_rank(4, rank, world)
@@ -92,6 +131,11 @@ def test_exchange_steps_gloo_world2():
 def test_single_process_degenerates():
     local = torch.ones((128, 4))
     assert PD.allgather_rows(local, 100, 128).shape == (100, 4)
+    assert PD.gather_rows_to_owner(local, 100, 128, 0).shape == (100, 4)
+    c = PD.WorkCounter()
+    assert [c.next() for _ in range(3)] == [0, 1, 2]
+    with pytest.raises(ValueError):
+        PD._raise_together(ValueError("x"))
     inl, tr, best = PD.reduce_best_hypothesis([torch.tensor(3), torch.tensor(9)], torch.zeros((2, 16), dtype=torch.float64),
                                               [0, 1], 2)
     assert best == 1 and inl.tolist() == [3, 9]

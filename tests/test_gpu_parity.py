@@ -303,10 +303,12 @@ def test_ransac_per_trial_counts_and_device_rng(O, D, torch):
     # no inliers at all (negative threshold) -> all-ones matrix and 0, as the reference (shape_context.py:120)
     a0, i0, t0, _ = D.ransac_affine(md, fd, 20, -1.0, 4, None, seed=1)
     assert i0.item() == 0 and torch.all(a0 == 1.0) and t0.item() == -1
-    # coplanar (degenerate) samples never win with NaNs
-    flat = md.clone(); flat[:, 2] = 5.0
-    a3, i3, _, _ = D.ransac_affine(flat, fd, 50, 16.0, 4, None, seed=2)
-    assert i3.item() == 0 and torch.all(torch.isfinite(a3))
+    # coplanar (degenerate) samples: numpy's pinv still answers (minimum-norm affine), so does the kernel; never NaN
+    mflat = m.copy(); mflat[2] = 5.0
+    idx3 = O.ransac_sample_indices(k, 4, 50, seed=2)
+    _, i3_o, per3_o, _ = O.do_ransac(mflat, f, 4, 50, 16, sample_indices=idx3, return_all=True)
+    a3, i3, _, per3 = D.ransac_affine(D.to_device_points(mflat), fd, 50, 16.0, 4, torch.from_numpy(idx3).cuda(), want_per_trial=True)
+    assert i3.item() == i3_o and np.array_equal(per3.cpu().numpy(), per3_o) and torch.all(torch.isfinite(a3))
 
 
 # ------------------------------------------------------------------------------ K6 + small ops

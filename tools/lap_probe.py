@@ -9,14 +9,17 @@ from platymatch_b200.synthetic import make_pair
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
 algo = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 2048
-p = make_pair(n, seed=n)
-dm, df = P.describe_cloud(p["moving"], 1), P.describe_cloud(p["fixed"], 4)
+dropout = float(sys.argv[4]) if len(sys.argv) > 4 else 0.10
+seed = int(sys.argv[5]) if len(sys.argv) > 5 else n
+p = make_pair(n, seed=seed, dropout=dropout)
+dm, df = P.describe_pair(p["moving"], p["fixed"], 1, 4)
 n1, n2 = dm.n, df.n
 cost = torch.empty((4, n1, (n2 + 3) // 4 * 4), dtype=torch.float32, device="cuda")
 for q, (a, b) in enumerate(P.HYPOTHESES_DISTINCT):
     D.chi2_cost(dm.operand(a), df.operand(b), out=cost[q])
 names = ["bid_rounds", "rows_after", "augment", "dijkstra", "status", "bids", "refreshes", "retries", "parked",
          "refresh_cyc", "auction_cyc", "bulk_bids", "sap_dense", "-", "-", "-"]
+print("n1 x n2 =", n1, "x", n2, flush=True)
 for batch in ([0], [1], [2], [3], [0, 1, 2, 3]):
     c = cost[batch].contiguous()
     for rep in range(3):
