@@ -40,7 +40,8 @@ struct PmLapView {
     const float *cost;      // [nr][ldc]
     double *u, *v;          // [nr], [nc]
     int32_t *row4col;       // [nc]
-    int32_t *col4row;       // [nr]  (caller's output buffer)
+    int32_t *col4row;       // [nr]  (workspace; rows >= nr_real are dummy rows; exported to the caller at the end)
+    int32_t *col4row_out;   // [nr_real] caller's output buffer
     int32_t *bid_col;       // [nr]
     double *bid_gamma;      // [nr]
     unsigned long long *colbest;  // [nc] winning bid key of the round (0 = no bid)
@@ -71,7 +72,7 @@ static inline size_t pm_lap_align(size_t x) { return (x + 255) & ~(size_t)255; }
 #define PM_LS_CTR_REFRESHES 12
 
 struct PmLapLayout {
-    size_t u, v, row4col, bid_col, bid_gamma, colbest, free_lists, counters, lcol, lcost, tau, width, ring, ring32, cell, per_item;
+    size_t col4row, u, v, row4col, bid_col, bid_gamma, colbest, free_lists, counters, lcol, lcost, tau, width, ring, ring32, cell, per_item;
 };
 
 static unsigned pm_ls_ring_cap(int nr) {   // power of two >= nr: the ring can hold every row at once
@@ -83,6 +84,7 @@ static unsigned pm_ls_ring_cap(int nr) {   // power of two >= nr: the ring can h
 static PmLapLayout pm_lap_layout(int nr, int nc) {
     PmLapLayout L;
     size_t o = 0;
+    L.col4row = o; o += pm_lap_align((size_t)nr * 4);
     L.u = o; o += pm_lap_align((size_t)nr * 8);
     L.v = o; o += pm_lap_align((size_t)nc * 8);
     L.row4col = o; o += pm_lap_align((size_t)nc * 4);
@@ -104,6 +106,9 @@ static PmLapLayout pm_lap_layout(int nr, int nc) {
 
 struct PmLapBatch {   // passed by value to kernels
     const float *cost; size_t cost_stride; int nr, nc, ncp, ldc;
+    int nr_real;            // rows of the caller's matrix; rows nr_real..nr-1 are DUMMY rows (all costs 0) that make a
+                            // problem with few slack columns square (nr == nc), see pm_lap_solve
+    const float *zero_row;  // [ldc] zeros: the cost row of every dummy row
     char *ws; PmLapLayout L;
     int32_t *col4row; long long *stats; double *total;
     int32_t *progress;   // [2] assignments made in the current / previous bidding round
@@ -115,7 +120,16 @@ struct PmLapBatch {   // passed by value to kernels
     int bulk_patience;   // bulk kernel: polls (200 ns apart) a warp waits for its ring slot before it leaves
     unsigned ring_cap;   // sparse auction: ticket ring capacity (power of two >= nr)
     int ring_in_smem;
+    // eps-scaling phases (problems without slack columns): increment = certified gap + eps, eps = eps_factor x the
+    // matrix' own cost scale (mean candidate-list width, accumulated by pm_ls_build_lists into scale[0..1] per matrix)
+    double eps_factor;   // 0 = exact phase (eps = 0)
+    double *scale;       // [batch][2]: sum of list widths, number of rows that contributed
 };
+
+// cost row of row i (dummy rows share one row of zeros)
+__device__ __forceinline__ const float *pm_lap_row(const float *cost, const PmLapBatch &B, int i) {
+    return i < B.nr_real ? cost + (size_t)i * B.ldc : B.zero_row;
+}
 
 __device__ __forceinline__ PmLapView pm_lap_view(const PmLapBatch &B, int b) {
     PmLapView V;
@@ -123,7 +137,8 @@ __device__ __forceinline__ PmLapView pm_lap_view(const PmLapBatch &B, int b) {
     V.cost = B.cost + (size_t)b * B.cost_stride;
     V.u = (double *)(w + B.L.u); V.v = (double *)(w + B.L.v);
     V.row4col = (int32_t *)(w + B.L.row4col);
-    V.col4row = B.col4row + (size_t)b * B.nr;
+    V.col4row = (int32_t *)(w + B.L.col4row);
+    V.col4row_out = B.col4row + (size_t)b * B.nr_real;
     V.bid_col = (int32_t *)(w + B.L.bid_col); V.bid_gamma = (double *)(w + B.L.bid_gamma);
     V.colbest = (unsigned long long *)(w + B.L.colbest);
     V.free_lists = (int32_t *)(w + B.L.free_lists);
@@ -146,11 +161,14 @@ __global__ void pm_lap_init_kernel(PmLapBatch B) {
         V.cell[j].price = 0.0; V.cell[j].owner = 0xFFFFFFFFu; V.cell[j].pad = 0u;
     }
     for (unsigned q = t; q < B.ring_cap; q += stride) V.ring32[q] = 0xFFFFFFFFu;
+    if (blockIdx.y == 0)
+        for (int j = t; j < B.ncp + 32; j += stride) const_cast<float *>(B.zero_row)[j] = 0.0f;
     if (t == 0) {
         V.counters[0] = B.nr; V.counters[1] = 0; V.counters[2] = 0; V.counters[3] = 0; V.counters[4] = 0;
         for (int k = 5; k < 16; ++k) V.counters[k] = 0;
         V.counters[PM_LS_CTR_LIVE] = B.bulk_warps;
         B.progress[0] = 0; B.progress[1] = 0;
+        B.scale[2 * blockIdx.y] = 0.0; B.scale[2 * blockIdx.y + 1] = 0.0;
         if (V.stats) for (int k = 0; k < PM_LAP_STATS; ++k) V.stats[k] = 0;
     }
 }
@@ -201,7 +219,7 @@ __global__ void __launch_bounds__(PM_LAP_BID_THREADS) pm_lap_bid_persistent(PmLa
             if (first < 0) first += gridDim.x;
             for (int idx = first; idx < nfree; idx += gridDim.x) {
                 const int i = __ldcg(&list[idx]);
-                const float *ci = V.cost + (size_t)i * B.ldc;
+                const float *ci = pm_lap_row(V.cost, B, i);
                 PmBid bid = {INFINITY, INFINITY, INT_MAX};
                 // two float4 sweeps per trip so that all loads of a thread are in flight together
                 for (int j0 = threadIdx.x * 4; j0 < B.nc; j0 += PM_LAP_BID_THREADS * 8) {
@@ -274,7 +292,7 @@ __global__ void __launch_bounds__(PM_LAP_BID_THREADS) pm_lap_bid_persistent(PmLa
                         const int prev = __ldcg(&V.row4col[j]);
                         const double vj = __ldcg(&V.v[j]) - gamma;
                         V.v[j] = vj;
-                        V.u[i] = (double)V.cost[(size_t)i * B.ldc + j] - vj;
+                        V.u[i] = (double)pm_lap_row(V.cost, B, i)[j] - vj;
                         V.row4col[j] = i;
                         V.col4row[i] = j;
                         V.colbest[j] = 0ull;
@@ -351,13 +369,21 @@ __device__ __forceinline__ void pm_ls_top_push(PmLsTop &t, double w, int j, floa
     }
 }
 
-// initial lists at zero prices: one warp per row, all SMs (float4 sweeps, ldc % 4 == 0)
+// Candidate lists of all rows at once: one warp per row, all SMs (float4 sweeps, ldc % 4 == 0).
+// AT_PRICES = false: the initial lists at zero prices; also accumulates the matrix' cost scale (mean list width).
+// AT_PRICES = true: lists at the prices the eps-scaling phases ended with (cells), plus the TIGHT FILTER that turns
+// the eps-optimal assignment into an exact warm start: a row keeps its column only if that column is an exact
+// arg-min of its row at these prices (complementary slackness with epsilon = 0); every other row is set free and
+// its column released.  (An eps-auction leaves the winning edge eps ABOVE the row's second best, so roughly half
+// of the rows are released; the exact phase re-seats them with ~1.3 bids each.)
+template <bool AT_PRICES>
 __global__ void __launch_bounds__(256) pm_ls_build_lists(PmLapBatch B) {
     const PmLapView V = pm_lap_view(B, blockIdx.y);
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
+    const double *prices = reinterpret_cast<const double *>(V.cell);      // first double of every 16-byte cell
     for (int i = warp; i < B.nr; i += nwarps) {
-        const float *ci = V.cost + (size_t)i * B.ldc;
+        const float *ci = pm_lap_row(V.cost, B, i);
         PmLsTop t;
         pm_ls_top_init(t);
 #pragma unroll 4
@@ -366,7 +392,10 @@ __global__ void __launch_bounds__(256) pm_ls_build_lists(PmLapBatch B) {
             const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-                if (j0 + e < B.nc) pm_ls_top_push(t, (double)cc[e], j0 + e, cc[e]);
+                if (j0 + e < B.nc) {
+                    const double w = AT_PRICES ? (double)cc[e] - __ldcg(prices + 2 * (size_t)(j0 + e)) : (double)cc[e];
+                    pm_ls_top_push(t, w, j0 + e, cc[e]);
+                }
         }
         double tmin = t.w[4], wmin = t.w[0];
 #pragma unroll
@@ -379,10 +408,86 @@ __global__ void __launch_bounds__(256) pm_ls_build_lists(PmLapBatch B) {
                       t.w[3] <= tmin ? t.j[3] : -1);
         reinterpret_cast<float4 *>(V.lcost + (size_t)i * PM_LS_K)[lane] = make_float4(t.c[0], t.c[1], t.c[2], t.c[3]);
         if (lane == 0) {
+            const double width = (tmin < INFINITY && wmin < INFINITY) ? tmin - wmin : INFINITY;
             V.tau[i] = tmin;
-            V.width[i] = (tmin < INFINITY && wmin < INFINITY) ? tmin - wmin : INFINITY;
+            V.width[i] = width;
+            if (!AT_PRICES && width < INFINITY && B.scale && i < B.nr_real) {     // (dummy rows have no cost scale)
+                atomicAdd(B.scale + 2 * blockIdx.y, width);
+                atomicAdd(B.scale + 2 * blockIdx.y + 1, 1.0);
+            }
+            if (AT_PRICES) {
+                const int a = V.col4row[i];
+                if (a >= 0) {
+                    const double wa = (double)ci[a] - __ldcg(prices + 2 * (size_t)a);
+                    if (!(wa <= wmin)) {                  // not an exact arg-min: release (each column has one owner)
+                        V.col4row[i] = -1;
+                        V.cell[a].owner = 0xFFFFFFFFu;
+                    }
+                }
+            }
         }
     }
+}
+
+// start of an eps-scaling phase: every row free again, prices kept (cells), queues empty
+__global__ void pm_ls_phase_reset_kernel(PmLapBatch B) {
+    const PmLapView V = pm_lap_view(B, blockIdx.y);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (int j = t; j < B.ncp; j += stride) V.cell[j].owner = 0xFFFFFFFFu;
+    for (int i = t; i < B.nr; i += stride) V.col4row[i] = -1;
+    for (unsigned q = t; q < B.ring_cap; q += stride) V.ring32[q] = 0xFFFFFFFFu;
+    if (t == 0) {
+        V.counters[PM_LS_CTR_FRESH] = 0; V.counters[PM_LS_CTR_HEAD] = 0; V.counters[PM_LS_CTR_TAIL] = 0;
+        V.counters[PM_LS_CTR_LIVE] = B.bulk_warps;
+    }
+}
+
+// After the last eps-scaling phase of a problem that was made square with dummy rows: make the dummies EXACTLY
+// tight before the exact phase.  A dummy (all costs zero) is indifferent between columns of equal price and tight on
+// its column only if no column is more expensive.  lambda = the lowest price among the dummy-held columns; every
+// column priced above lambda is lowered to lambda (prices only ever fall, so the candidate lists stay certified);
+// a real row that held such a column is released (its edge is no longer tight) and re-seated by the exact phase.
+// Afterwards all dummy-held columns cost lambda = the maximum price: complementary slackness holds exactly for them.
+__global__ void __launch_bounds__(1024) pm_ls_equalise_dummies_kernel(PmLapBatch B) {
+    const PmLapView V = pm_lap_view(B, blockIdx.x);
+    __shared__ double red[32];
+    __shared__ double s_lambda;
+    double lam = INFINITY;
+    for (int d = B.nr_real + threadIdx.x; d < B.nr; d += blockDim.x) {
+        const int j = V.col4row[d];
+        if (j >= 0) lam = fmin(lam, V.cell[j].price);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lam = fmin(lam, __shfl_xor_sync(0xffffffffu, lam, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lam;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        lam = red[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lam = fmin(lam, __shfl_xor_sync(0xffffffffu, lam, o));
+        if (threadIdx.x == 0) s_lambda = lam;
+    }
+    __syncthreads();
+    lam = s_lambda;
+    if (!(lam < INFINITY)) return;              // no dummy is seated (phase cut short): nothing to equalise
+    for (int j = threadIdx.x; j < B.nc; j += blockDim.x) {
+        if (V.cell[j].price > lam) {
+            V.cell[j].price = lam;
+            const unsigned r = V.cell[j].owner;
+            if (r != 0xFFFFFFFFu && (int)r < B.nr_real) {
+                V.cell[j].owner = 0xFFFFFFFFu;
+                V.col4row[r] = -1;
+            }
+        }
+    }
+}
+
+// eps of this launch for one matrix (0 in the exact phases)
+__device__ __forceinline__ double pm_ls_eps(const PmLapBatch &B, int b) {
+    if (!(B.eps_factor > 0.0)) return 0.0;
+    const double sum = __ldcg(B.scale + 2 * b), cnt = __ldcg(B.scale + 2 * b + 1);
+    const double scale = cnt > 0.0 ? sum / cnt : 0.0;
+    return (scale > 0.0 && scale < INFINITY) ? B.eps_factor * scale : 0.0;
 }
 
 // order-preserving 64-bit integer image of a double (so that REDUX.MIN on two 32-bit halves finds the minimum)
@@ -499,6 +604,7 @@ __global__ void __launch_bounds__(256) pm_ls_bulk_kernel(PmLapBatch B, int ctas_
     volatile unsigned *ring = V.ring32;
     const unsigned ring_mask = B.ring_cap - 1;
     volatile int *ctr = V.counters;
+    const double eps = pm_ls_eps(B, blockIdx.x / ctas_per_matrix);
     int bids = 0, retries = 0, dropped = 0, refreshes = 0;
     int carry = -1;
     while (bids < B.max_bids) {
@@ -528,27 +634,54 @@ __global__ void __launch_bounds__(256) pm_ls_bulk_kernel(PmLapBatch B, int ctas_
             row = __shfl_sync(0xffffffffu, row, 0);
             if (row < 0) break;
         }
-        int4 cj = __ldcg(reinterpret_cast<const int4 *>(V.lcol + (size_t)row * PM_LS_K) + lane);
-        float4 cc = __ldcg(reinterpret_cast<const float4 *>(V.lcost + (size_t)row * PM_LS_K) + lane);
-        double tau = __ldcg(V.tau + row);
+        // A DUMMY row (row >= nr_real: all costs zero, present when a problem with few slack columns was made
+        // square) has no use for a candidate list: its reduced values are just the negated prices, so it bids
+        // from one sweep over the price cells (exact best / second best, no certificate needed).
+        const bool dummy = row >= B.nr_real;
+        int4 cj = make_int4(-1, -1, -1, -1);
+        float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
+        double tau = INFINITY;
+        if (!dummy) {
+            cj = __ldcg(reinterpret_cast<const int4 *>(V.lcol + (size_t)row * PM_LS_K) + lane);
+            cc = __ldcg(reinterpret_cast<const float4 *>(V.lcost + (size_t)row * PM_LS_K) + lane);
+            tau = __ldcg(V.tau + row);
+        }
         bool fresh = false, won = false;
         while (true) {
-            const int js[4] = {cj.x, cj.y, cj.z, cj.w};
-            const float cs[4] = {cc.x, cc.y, cc.z, cc.w};
-            double vs[4], ws[4];
-            unsigned os[4];
+            double w1, w2, v1 = 0.0;        // lane-local: best and second-best reduced value, price / owner of the best
+            int bj = -1;
+            unsigned own = 0xFFFFFFFFu;
+            if (dummy) {
+                w1 = INFINITY; w2 = INFINITY;
+#pragma unroll 4
+                for (int j = lane; j < nc; j += 32) {
+                    const ulonglong2 c = __ldcv(reinterpret_cast<const ulonglong2 *>(&cell[j]));
+                    const double vj = __longlong_as_double((long long)c.x), w = -vj;
+                    if (w < w1) { w2 = w1; w1 = w; bj = j; v1 = vj; own = (unsigned)c.y; }
+                    else if (w < w2) w2 = w;
+                }
+            } else {
+                const int js[4] = {cj.x, cj.y, cj.z, cj.w};
+                const float cs[4] = {cc.x, cc.y, cc.z, cc.w};
+                double vs[4], ws[4];
+                unsigned os[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {       // {price, owner} of the cell in one 16-byte load
-                const ulonglong2 c = __ldcv(reinterpret_cast<const ulonglong2 *>(&cell[js[e] < 0 ? 0 : js[e]]));
-                vs[e] = __longlong_as_double((long long)c.x);
-                os[e] = (unsigned)c.y;
-                const double w = (double)cs[e] - vs[e];
-                ws[e] = js[e] < 0 ? INFINITY : w;
+                for (int e = 0; e < 4; ++e) {       // {price, owner} of the cell in one 16-byte load
+                    const ulonglong2 c = __ldcv(reinterpret_cast<const ulonglong2 *>(&cell[js[e] < 0 ? 0 : js[e]]));
+                    vs[e] = __longlong_as_double((long long)c.x);
+                    os[e] = (unsigned)c.y;
+                    const double w = (double)cs[e] - vs[e];
+                    ws[e] = js[e] < 0 ? INFINITY : w;
+                }
+                const double lo01 = fmin(ws[0], ws[1]), hi01 = fmax(ws[0], ws[1]);
+                const double lo23 = fmin(ws[2], ws[3]), hi23 = fmax(ws[2], ws[3]);
+                w1 = fmin(lo01, lo23);
+                w2 = fmin(fmax(lo01, lo23), fmin(hi01, hi23));
+                const bool m0 = ws[0] == w1, m1 = ws[1] == w1, m2 = ws[2] == w1;
+                bj = m0 ? js[0] : m1 ? js[1] : m2 ? js[2] : js[3];
+                v1 = m0 ? vs[0] : m1 ? vs[1] : m2 ? vs[2] : vs[3];
+                own = m0 ? os[0] : m1 ? os[1] : m2 ? os[2] : os[3];
             }
-            const double lo01 = fmin(ws[0], ws[1]), hi01 = fmax(ws[0], ws[1]);
-            const double lo23 = fmin(ws[2], ws[3]), hi23 = fmax(ws[2], ws[3]);
-            const double w1 = fmin(lo01, lo23);
-            const double w2 = fmin(fmax(lo01, lo23), fmin(hi01, hi23));
             const unsigned long long k1 = pm_ordkey(w1);
             const unsigned long long kb = pm_warp_min_u64(k1);
             const int hl = __ffs(__ballot_sync(0xffffffffu, k1 == kb)) - 1;
@@ -559,7 +692,7 @@ __global__ void __launch_bounds__(256) pm_ls_bulk_kernel(PmLapBatch B, int ctas_
             if (!(bw < tau) && !(fresh && bw <= tau)) {     // list exhausted: rebuild from the dense row
                 double width = __ldcg(V.width + row), wmin;
                 if (!(width > 0.0) || !(width < INFINITY)) width = fabs(tau) * 1e-3 + 1e-300;
-                const float *ci = V.cost + (size_t)row * B.ldc;
+                const float *ci = pm_lap_row(V.cost, B, row);
                 const double *prices = reinterpret_cast<const double *>(cell);
                 int n = pm_ls_refresh_row<true>(V, row, ci, prices, nc, lane, tau + width, cj, cc, tau, wmin);
                 if (n < 8 && wmin < INFINITY) {
@@ -576,13 +709,10 @@ __global__ void __launch_bounds__(256) pm_ls_bulk_kernel(PmLapBatch B, int ctas_
             }
             double gamma = fmin(sw, tau) - bw;
             if (!(gamma > 0.0)) gamma = 0.0;
+            gamma += eps;                                   // (eps-scaling phases; 0 in the exact phases)
             int result = PM_LS_RETRY;
             unsigned prev = 0xFFFFFFFFu;
             if (holder) {
-                const bool m0 = ws[0] == w1, m1 = ws[1] == w1, m2 = ws[2] == w1;
-                const int bj = m0 ? js[0] : m1 ? js[1] : m2 ? js[2] : js[3];
-                const double v1 = m0 ? vs[0] : m1 ? vs[1] : m2 ? vs[2] : vs[3];
-                const unsigned own = m0 ? os[0] : m1 ? os[1] : m2 ? os[2] : os[3];
                 if (gamma == 0.0 && own != 0xFFFFFFFFu) result = PM_LS_PARK;            // zero-increment steal
                 else if (pm_ls_cas128(&cell[bj], v1, own, v1 - gamma, (unsigned)row)) {
                     result = PM_LS_WON;
@@ -671,6 +801,7 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
         if (t == 0) S.tail = (unsigned)s_scan[32];
         __syncthreads();
     }
+    const double eps = pm_ls_eps(B, blockIdx.x);
     long long bids = 0, refreshes = 0, retries = 0, parked = 0, refresh_cycles = 0;
     const long long t_begin = clock64();
     int carry = -1;          // displaced owner this warp continues with (only when nothing is queued)
@@ -700,27 +831,48 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
             row = __shfl_sync(0xffffffffu, row, 0);
             if (row < 0) break;
         }
-        int4 cj = __ldcg(reinterpret_cast<const int4 *>(V.lcol + (size_t)row * PM_LS_K) + lane);
-        float4 cc = __ldcg(reinterpret_cast<const float4 *>(V.lcost + (size_t)row * PM_LS_K) + lane);
-        double tau = __ldcg(V.tau + row);
+        const bool dummy = row >= B.nr_real;          // zero-cost row: bids from one sweep over the prices (see the bulk kernel)
+        int4 cj = make_int4(-1, -1, -1, -1);
+        float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
+        double tau = INFINITY;
+        if (!dummy) {
+            cj = __ldcg(reinterpret_cast<const int4 *>(V.lcol + (size_t)row * PM_LS_K) + lane);
+            cc = __ldcg(reinterpret_cast<const float4 *>(V.lcost + (size_t)row * PM_LS_K) + lane);
+            tau = __ldcg(V.tau + row);
+        }
         bool fresh = false;
         int result, prev = PM_LS_NONE;
         while (true) {
-            // lane-local: reduced values of its 4 slots at the current prices, branch-free
-            const int js[4] = {cj.x, cj.y, cj.z, cj.w};
-            const float cs[4] = {cc.x, cc.y, cc.z, cc.w};
-            double vs[4], ws[4];
+            double w1, w2, v1 = 0.0;        // lane-local: best and second-best reduced value, price of the best
+            int bj = -1;
+            if (dummy) {
+                w1 = INFINITY; w2 = INFINITY;
+#pragma unroll 4
+                for (int j = lane; j < nc; j += 32) {
+                    const double vj = *reinterpret_cast<volatile double *>(&v[j]), w = -vj;
+                    if (w < w1) { w2 = w1; w1 = w; bj = j; v1 = vj; }
+                    else if (w < w2) w2 = w;
+                }
+            } else {
+                // its 4 list slots at the current prices, branch-free
+                const int js[4] = {cj.x, cj.y, cj.z, cj.w};
+                const float cs[4] = {cc.x, cc.y, cc.z, cc.w};
+                double vs[4], ws[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                vs[e] = *reinterpret_cast<volatile double *>(&v[js[e] < 0 ? 0 : js[e]]);
-                const double w = (double)cs[e] - vs[e];
-                ws[e] = js[e] < 0 ? INFINITY : w;
+                for (int e = 0; e < 4; ++e) {
+                    vs[e] = *reinterpret_cast<volatile double *>(&v[js[e] < 0 ? 0 : js[e]]);
+                    const double w = (double)cs[e] - vs[e];
+                    ws[e] = js[e] < 0 ? INFINITY : w;
+                }
+                // smallest and second smallest of four: 7 min/max
+                const double lo01 = fmin(ws[0], ws[1]), hi01 = fmax(ws[0], ws[1]);
+                const double lo23 = fmin(ws[2], ws[3]), hi23 = fmax(ws[2], ws[3]);
+                w1 = fmin(lo01, lo23);
+                w2 = fmin(fmax(lo01, lo23), fmin(hi01, hi23));
+                const bool m0 = ws[0] == w1, m1 = ws[1] == w1, m2 = ws[2] == w1;
+                bj = m0 ? js[0] : m1 ? js[1] : m2 ? js[2] : js[3];
+                v1 = m0 ? vs[0] : m1 ? vs[1] : m2 ? vs[2] : vs[3];
             }
-            // smallest and second smallest of four: 7 min/max
-            const double lo01 = fmin(ws[0], ws[1]), hi01 = fmax(ws[0], ws[1]);
-            const double lo23 = fmin(ws[2], ws[3]), hi23 = fmax(ws[2], ws[3]);
-            const double w1 = fmin(lo01, lo23);
-            const double w2 = fmin(fmax(lo01, lo23), fmin(hi01, hi23));
             // warp: best value (REDUX on order-preserving keys), one holder lane, second best
             const unsigned long long k1 = pm_ordkey(w1);
             const unsigned long long kb = pm_warp_min_u64(k1);
@@ -736,10 +888,10 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
                 const long long t0 = clock64();
                 double width = __ldcg(V.width + row), wmin;
                 if (!(width > 0.0) || !(width < INFINITY)) width = fabs(tau) * 1e-3 + 1e-300;
-                int n = pm_ls_refresh_row<false>(V, row, V.cost + (size_t)row * B.ldc, v, nc, lane, tau + width, cj, cc, tau, wmin);
+                int n = pm_ls_refresh_row<false>(V, row, pm_lap_row(V.cost, B, row), v, nc, lane, tau + width, cj, cc, tau, wmin);
                 if (n < 8 && wmin < INFINITY) {        // window too narrow (prices moved a lot): centre it on the minimum
                     width *= 4.0;
-                    n = pm_ls_refresh_row<false>(V, row, V.cost + (size_t)row * B.ldc, v, nc, lane, wmin + width, cj, cc, tau, wmin);
+                    n = pm_ls_refresh_row<false>(V, row, pm_lap_row(V.cost, B, row), v, nc, lane, wmin + width, cj, cc, tau, wmin);
                 } else if (n >= PM_LS_K) {
                     width *= 0.5;
                 }
@@ -751,11 +903,9 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
             }
             double gamma = fmin(sw, tau) - bw;    // certified lower bound of the true increment
             if (!(gamma > 0.0)) gamma = 0.0;
+            gamma += eps;                         // (eps-scaling phases; 0 in the exact phases)
             result = PM_LS_RETRY;
             if (holder) {
-                const bool m0 = ws[0] == w1, m1 = ws[1] == w1, m2 = ws[2] == w1;
-                const int bj = m0 ? js[0] : m1 ? js[1] : m2 ? js[2] : js[3];
-                const double v1 = m0 ? vs[0] : m1 ? vs[1] : m2 ? vs[2] : vs[3];
                 unsigned short *p = &owner[bj];
                 unsigned short old;
                 while (true) {      // lock the column: the owner word doubles as the lock
@@ -814,23 +964,30 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
         const unsigned short r = owner[j];
         if (j < nc) {
             V.v[j] = v[j];
+            V.cell[j].price = v[j];               // (the next eps-scaling phase / the tight filter read the cells)
+            V.cell[j].owner = (r == PM_LS_NONE) ? 0xFFFFFFFFu : (unsigned)r;
             V.row4col[j] = (r == PM_LS_NONE) ? -1 : (int)r;
             if (r != PM_LS_NONE) {
                 V.col4row[r] = j;
-                V.u[r] = (double)V.cost[(size_t)r * B.ldc + j] - v[j];
+                V.u[r] = (double)pm_lap_row(V.cost, B, r)[j] - v[j];
             }
         }
     }
     if (t == 0) {
         V.counters[3] = (int32_t)(S.maxbids > 0x7fffffffull ? 0x7fffffffull : S.maxbids);
-        if (V.stats) {
-            V.stats[PM_LAP_STAT_BIDS] = (long long)S.stat[0] + V.counters[PM_LS_CTR_BIDS];
+        if (V.stats) {      // accumulated over the launches of this solve (eps-scaling phases + exact phase)
+            V.stats[PM_LAP_STAT_BIDS] += (long long)S.stat[0];
             V.stats[PM_LAP_STAT_BULK_BIDS] = V.counters[PM_LS_CTR_BIDS];
-            V.stats[PM_LAP_STAT_REFRESHES] = (long long)S.stat[1] + V.counters[PM_LS_CTR_REFRESHES];
-            V.stats[PM_LAP_STAT_RETRIES] = (long long)S.stat[2] + V.counters[PM_LS_CTR_RETRIES];
+            V.stats[PM_LAP_STAT_REFRESHES] += (long long)S.stat[1];
+            V.stats[PM_LAP_STAT_RETRIES] += (long long)S.stat[2];
             V.stats[PM_LAP_STAT_PARKED] = (long long)S.stat[3];
-            V.stats[PM_LAP_STAT_REFRESH_CYCLES] = (long long)S.stat[4];
-            V.stats[PM_LAP_STAT_AUCTION_CYCLES] = (long long)S.stat[5];
+            V.stats[PM_LAP_STAT_REFRESH_CYCLES] += (long long)S.stat[4];
+            V.stats[PM_LAP_STAT_AUCTION_CYCLES] += (long long)S.stat[5];
+            if (!(B.eps_factor > 0.0)) {     // last auction launch of the solve: fold the bulk kernels' counters in
+                V.stats[PM_LAP_STAT_BIDS] += V.counters[PM_LS_CTR_BIDS];
+                V.stats[PM_LAP_STAT_REFRESHES] += V.counters[PM_LS_CTR_REFRESHES];
+                V.stats[PM_LAP_STAT_RETRIES] += V.counters[PM_LS_CTR_RETRIES];
+            }
         }
     }
 }
@@ -910,7 +1067,7 @@ __global__ void __launch_bounds__(PM_LAP_MAX_THREADS, 1) pm_lap_sap_kernel(PmLap
 #pragma unroll
         for (int q = 0; q < CPT; ++q) d[q] = INFINITY;
         while (true) {
-            const float *ci = V.cost + (size_t)i * ldc;
+            const float *ci = pm_lap_row(V.cost, B, i);
             const double ui = V.u[i];
             double best = INFINITY;
             int best_tie = INT_MAX;
@@ -918,7 +1075,7 @@ __global__ void __launch_bounds__(PM_LAP_MAX_THREADS, 1) pm_lap_sap_kernel(PmLap
             for (int g = 0; g < CPT / 4; ++g) {
                 const int c0 = g * group_stride + t * 4;
                 float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c0 < ldc) c4 = *reinterpret_cast<const float4 *>(ci + c0);
+                if (c0 < B.ncp) c4 = *reinterpret_cast<const float4 *>(ci + c0);      // (ncp <= ldc; the dummy rows' zero row has ncp + 32 floats)
                 double2 va = make_double2(0.0, 0.0), vb = make_double2(0.0, 0.0);
                 if (!V_IN_REGS && c0 < nc) {   // v padded to a multiple of 4 doubles in the workspace
                     va = *reinterpret_cast<const double2 *>(V.v + c0);
@@ -997,8 +1154,9 @@ __global__ void __launch_bounds__(PM_LAP_MAX_THREADS, 1) pm_lap_sap_kernel(PmLap
     // total cost, float64, fixed order
     __syncthreads();
     double tot = 0.0;
-    for (int r = t; r < nr; r += nthreads) {
+    for (int r = t; r < B.nr_real; r += nthreads) {       // dummy rows cost nothing and are not reported
         const int c = V.col4row[r];
+        V.col4row_out[r] = c;
         if (c >= 0) tot += (double)V.cost[(size_t)r * ldc + c];
     }
     tot = pm_block_sum(tot, &s_val[0][0]);
@@ -1152,7 +1310,7 @@ __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmL
                 __syncthreads();                               // everybody has read s_lam
                 const int il = tree_row[lam_idx];
                 const double dl = tree_dist[lam_idx], uil = __ldcg(V.u + il);
-                const float *ci = V.cost + (size_t)il * ldc;
+                const float *ci = pm_lap_row(V.cost, B, il);
                 for (int j = t; j < nc; j += PM_SS_THREADS) {
                     if (!scanned[j]) {
                         const double r = ((dl + (double)ci[j]) - uil) - v[j];
@@ -1210,8 +1368,9 @@ __global__ void __launch_bounds__(PM_SS_THREADS, 1) pm_lap_sap_sparse_kernel(PmL
     }
     __syncthreads();
     double tot = 0.0;
-    for (int r = t; r < nr; r += PM_SS_THREADS) {
+    for (int r = t; r < B.nr_real; r += PM_SS_THREADS) {   // dummy rows cost nothing and are not reported
         const int c = V.col4row[r];
+        V.col4row_out[r] = c;
         if (c >= 0) tot += (double)V.cost[(size_t)r * ldc + c];
     }
     tot = pm_block_sum(tot, &s_val[0][0]);
@@ -1254,10 +1413,15 @@ static int pm_lap_raise_smem_limit(K kernel, int smem_optin, int dev) {
     return pm_lap_raise_smem_limit_impl((const void *)kernel, smem_optin, dev);
 }
 
+// header: progress counters | per-matrix cost scale [batch][2] f64 | one row of zeros (the dummy rows' cost row)
+static size_t pm_lap_header_bytes(int batch, int ncp) {
+    return 256 + pm_lap_align((size_t)batch * 2 * sizeof(double)) + pm_lap_align((size_t)(ncp + 32) * sizeof(float));
+}
+
 extern "C" size_t pm_lap_workspace_bytes(int batch, int nr, int nc) {
     if (batch < 1 || nr < 1 || nc < 1) return 0;
     const int ncp = (nc + 3) & ~3;
-    return 256 + (size_t)batch * pm_lap_layout(nr, ncp).per_item;
+    return pm_lap_header_bytes(batch, ncp) + (size_t)batch * pm_lap_layout(nc, ncp).per_item;
 }
 
 template <int CPT, bool VR>
@@ -1278,6 +1442,7 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
     PM_REQUIRE(batch >= 1 && nr >= 1 && nc >= 1, "empty problem");
     PM_REQUIRE(nr <= nc, "need nr <= nc (transpose on the host side, as scipy does)");
     PM_REQUIRE(ldc >= nc && ldc % 4 == 0, "ldc must be >= nc and a multiple of 4");
+    // (the dense kernels read a row in float4 sweeps up to the column count rounded up to 4, never further)
     PM_REQUIRE((reinterpret_cast<size_t>(cost) & 15) == 0, "cost must be 16-byte aligned");
     PM_REQUIRE(max_bid_rounds >= 0, "max_bid_rounds < 0");
     PM_REQUIRE(algorithm >= PM_LAP_ALGO_AUTO && algorithm <= PM_LAP_ALGO_DENSE_AUCTION, "unknown algorithm");
@@ -1292,16 +1457,32 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
     }
     cudaStream_t s = pm_stream(stream);
     PmLapBatch B;
-    B.cost = cost; B.cost_stride = (size_t)nr * ldc; B.nr = nr; B.nc = nc; B.ldc = ldc;
+    B.cost = cost; B.cost_stride = (size_t)nr * ldc; B.nr = nr; B.nr_real = nr; B.nc = nc; B.ldc = ldc;
     B.ncp = (nc + 3) & ~3;
-    B.L = pm_lap_layout(nr, B.ncp);
+    // Few slack columns (and none): solved as a SQUARE problem with nc - nr dummy rows of zero cost, eps-scaling first
+    // (see below).  The dummies take the columns that stay unassigned, so the optimum over the real rows is the same.
+    bool square = false;
+    if (max_bid_rounds > 0 && algorithm != PM_LAP_ALGO_DENSE_AUCTION && nr >= 64) {
+        double max_slack = 0.08;                              // of nc; above it the pure epsilon = 0 schedule is faster
+        const char *e = getenv("PM_LAP_SQUARE_SLACK");
+        if (e) max_slack = atof(e);
+        square = (double)(nc - nr) <= max_slack * (double)nc;
+        e = getenv("PM_LAP_EPS_SCALING");
+        if (e) square = atoi(e) != 0;
+    }
+    if (square) B.nr = nc;
+    B.L = pm_lap_layout(nc, B.ncp);                           // (sized for the square case: rows <= nc)
     B.progress = (int32_t *)workspace;
-    B.ws = (char *)workspace + 256;
+    B.scale = (double *)((char *)workspace + 256);
+    B.zero_row = (const float *)((char *)workspace + 256 + pm_lap_align((size_t)batch * 2 * sizeof(double)));
+    B.eps_factor = 0.0;
+    B.ws = (char *)workspace + pm_lap_header_bytes(batch, B.ncp);
     B.col4row = col4row; B.stats = (long long *)stats; B.total = total;
     // one "round" of the sparse auction = a budget of one bid per row, spread over the 32 warps
-    B.max_bids = ((long long)max_bid_rounds * nr + 31) / 32;
+    const int rows = B.nr;                               // incl. the dummy rows of a squared problem
+    B.max_bids = ((long long)max_bid_rounds * rows + 31) / 32;
     B.max_bids_tail = B.max_bids;
-    int bulk_ctas = (nr + 127) / 128;                    // 8 warps per CTA: ~16 rows per warp at the start
+    int bulk_ctas = (rows + 127) / 128;                    // 8 warps per CTA: ~16 rows per warp at the start
     if (bulk_ctas > 64) bulk_ctas = 64;
     {
         const char *e = getenv("PM_LAP_STOP_LIVE");      // tuning knobs
@@ -1315,7 +1496,7 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
         // (nr == nc) need an order of magnitude more, almost all of them in long sequential price wars that the
         // augmenting-path phase settles much faster: cap the auction at ~64 bids per row (bulk) + ~16 (tail),
         // with a 4x allowance for imbalance between warps.
-        const long long cap_bulk = 4ll * 64 * nr / B.bulk_warps, cap_tail = 4ll * 16 * nr / 32;
+        const long long cap_bulk = 4ll * 64 * rows / B.bulk_warps, cap_tail = 4ll * 16 * rows / 32;
         if (B.max_bids > (cap_bulk > 1024 ? cap_bulk : 1024)) B.max_bids = cap_bulk > 1024 ? cap_bulk : 1024;
         if (B.max_bids_tail > (cap_tail > 1024 ? cap_tail : 1024)) B.max_bids_tail = cap_tail > 1024 ? cap_tail : 1024;
         e = getenv("PM_LAP_BULK_PATIENCE");
@@ -1326,8 +1507,8 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
     PM_CUDA_TRY(cudaGetDevice(&dev));
     PM_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     size_t ls_smem = pm_ls_smem_bytes(B.ncp);
-    const bool sparse_fits = nr <= (int)PM_LS_MAX_ROWS && ls_smem + 2048 <= (size_t)smem_optin;
-    B.ring_cap = pm_ls_ring_cap(nr);
+    const bool sparse_fits = rows <= (int)PM_LS_MAX_ROWS && ls_smem + 2048 <= (size_t)smem_optin;
+    B.ring_cap = pm_ls_ring_cap(rows);
     B.ring_in_smem = ls_smem + (size_t)B.ring_cap * 2 + 2048 <= (size_t)smem_optin;
     if (B.ring_in_smem) ls_smem += (size_t)B.ring_cap * 2;
     if (algorithm == PM_LAP_ALGO_SPARSE_AUCTION && !sparse_fits) {
@@ -1335,25 +1516,68 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
         return PM_ERR_UNSUPPORTED;
     }
     if (algorithm == PM_LAP_ALGO_AUTO) algorithm = sparse_fits ? PM_LAP_ALGO_SPARSE_AUCTION : PM_LAP_ALGO_DENSE_AUCTION;
+    if (algorithm != PM_LAP_ALGO_SPARSE_AUCTION && square) { square = false; B.nr = nr; }   // (only the sparse auction bids for dummy rows)
 
     pm_lap_init_kernel<<<dim3(32, batch), 256, 0, s>>>(B);
     PM_LAUNCH_CHECK();
     if (max_bid_rounds > 0 && algorithm == PM_LAP_ALGO_SPARSE_AUCTION) {
         int sms = 0;
         PM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        int blocks = (nr + 7) / 8;                       // 8 warps (rows) per CTA per sweep
+        int blocks = (rows + 7) / 8;                       // 8 warps (rows) per CTA per sweep
         const int cap = (sms * 8 + batch - 1) / batch;   // ~8 resident CTAs per SM over the whole batch
         if (blocks > cap) blocks = cap;
-        pm_ls_build_lists<<<dim3(blocks, batch), 256, 0, s>>>(B);
-        PM_LAUNCH_CHECK();
-        pm_ls_bulk_kernel<<<batch * bulk_ctas, 256, 0, s>>>(B, bulk_ctas);
+        pm_ls_build_lists<false><<<dim3(blocks, batch), 256, 0, s>>>(B);
         PM_LAUNCH_CHECK();
         // the tail kernel is issue-bound: ask for more than half of an SM's shared memory so that two of its
         // 1024-thread CTAs (a batch of matrices) are never placed on the same SM
         size_t tail_smem = ls_smem;
         if (tail_smem < 120 * 1024 && (size_t)smem_optin >= 120 * 1024 + 2048) tail_smem = 120 * 1024;
         if (int rc = pm_lap_raise_smem_limit(pm_ls_auction_kernel, smem_optin, dev)) return rc;
-        pm_ls_auction_kernel<<<batch, 1024, tail_smem, s>>>(B);
+        // Problems WITHOUT slack columns (nr == nc: every column must be sold) are where an epsilon = 0 auction
+        // degenerates into long sequential price wars (8000 x 8000: seconds).  They get eps-scaling first: a few
+        // phases of the same certified bids with increment + eps (eps = a fraction of the matrix' own cost scale,
+        // divided by theta from phase to phase; every phase restarts with all rows free and keeps the prices), which
+        // brings the prices within eps of an optimal dual solution with ~30 bids per row in total, all of them with
+        // thousands of rows bidding in parallel.  The tight filter (pm_ls_build_lists<true>) then keeps the exactly
+        // tight edges as the warm start of the exact (epsilon = 0) phase + augmenting paths below, so the result is
+        // the exact optimum as before.  (With slack columns the prices of columns that end up unassigned would have
+        // to return to zero, which eps-scaling cannot guarantee: those keep the pure epsilon = 0 schedule.)
+        const bool eps_scaling = square;
+        if (eps_scaling) {
+            double factor = 1.0 / 16.0, theta = 8.0;
+            int phases = 6;
+            const char *e = getenv("PM_LAP_EPS0");
+            if (e && atof(e) > 0.0) factor = atof(e);
+            e = getenv("PM_LAP_EPS_THETA");
+            if (e && atof(e) > 1.0) theta = atof(e);
+            e = getenv("PM_LAP_EPS_PHASES");
+            if (e && atoi(e) > 0) phases = atoi(e);
+            const int stop_live = B.stop_live;
+            B.stop_live = 0;                                  // a phase runs to completion
+            for (int k = 0; k < phases; ++k, factor /= theta) {
+                B.eps_factor = factor;
+                if (k > 0) {
+                    pm_ls_phase_reset_kernel<<<dim3(32, batch), 256, 0, s>>>(B);
+                    PM_LAUNCH_CHECK();
+                }
+                pm_ls_bulk_kernel<<<batch * bulk_ctas, 256, 0, s>>>(B, bulk_ctas);
+                PM_LAUNCH_CHECK();
+                pm_ls_auction_kernel<<<batch, 1024, tail_smem, s>>>(B);
+                PM_LAUNCH_CHECK();
+            }
+            B.eps_factor = 0.0;
+            B.stop_live = stop_live;
+            if (B.nr > B.nr_real) {
+                pm_ls_equalise_dummies_kernel<<<batch, 1024, 0, s>>>(B);
+                PM_LAUNCH_CHECK();
+            }
+            pm_ls_build_lists<true><<<dim3(blocks, batch), 256, 0, s>>>(B);       // lists at these prices + tight filter
+            PM_LAUNCH_CHECK();
+        } else {
+            pm_ls_bulk_kernel<<<batch * bulk_ctas, 256, 0, s>>>(B, bulk_ctas);
+            PM_LAUNCH_CHECK();
+        }
+        pm_ls_auction_kernel<<<batch, 1024, tail_smem, s>>>(B);                   // exact phase (rest of it)
         PM_LAUNCH_CHECK();
     } else if (max_bid_rounds > 0) {
         int sms = 0, per_sm = 0;
