@@ -11,6 +11,7 @@
 // {count, sum z, sum y, sum x}.  The sums are exact integers, so mean = sum / count rounds once and
 // equals np.mean of the integer coordinates bit for bit (sums stay far below 2^53).
 // A second small kernel compacts the non-empty ids in ascending order (np.unique order).
+#include <stdlib.h>
 #include "pm_common.cuh"
 
 template <typename T>
@@ -155,6 +156,99 @@ __global__ void __launch_bounds__(256) pm_label_accumulate_kernel(const T *__res
     }
 }
 
+// ---- round 2: the streaming kernel -------------------------------------------------------------------------
+// The kernel above is bound by instruction issue (~300 instructions per 16 voxels in volumes where every other
+// 128-voxel run touches a nucleus: warp votes, REDUX groups, carry arithmetic for the voxel coordinates on every load).
+// A label volume is ~98 % background, so this one spends ~8 instructions per 16-byte chunk on the common case and
+// does everything else per THREAD, only for chunks that contain foreground: no warp collective anywhere (a chunk
+// is 4 / 8 consecutive voxels of one thread), the voxel coordinates come from two divisions when they are needed,
+// and the chunk's voxels are run-length merged (same id, same image row) into items {count, k z, k y, sum x} that are
+// added with four fire-and-forget 64-bit reductions.  Same exact integer sums as before.
+template <typename T>
+__device__ __noinline__ void pm_label_chunk(const uint4 q, size_t v0, unsigned plane, unsigned ny, unsigned nx,
+                                            unsigned table_size, unsigned long long *__restrict__ acc) {
+    constexpr int VPC = 16 / (int)sizeof(T);
+    int ids[VPC];
+    if (sizeof(T) == 4) {
+        ids[0] = (int)q.x; ids[1] = (int)q.y; ids[2] = (int)q.z; ids[3] = (int)q.w;
+    } else {
+        const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < VPC; ++e) ids[e] = (int)((w[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
+    }
+    unsigned pz = (unsigned)(v0 / plane);
+    const unsigned rem = (unsigned)(v0 - (size_t)pz * plane);
+    unsigned py = rem / nx, px = rem - py * nx;
+    int run_id = 0;
+    unsigned k = 0, sx = 0, ry = 0, rz = 0;
+#pragma unroll
+    for (int e = 0; e < VPC; ++e) {
+        const int id = ids[e];
+        const bool valid = id > 0 && (unsigned)id < table_size;
+        if (k && (!valid || id != run_id || py != ry || pz != rz)) {          // the run ends: flush it
+            unsigned long long *a = acc + (size_t)run_id * 4;
+            atomicAdd(a + 0, (unsigned long long)k);
+            atomicAdd(a + 1, (unsigned long long)k * rz);
+            atomicAdd(a + 2, (unsigned long long)k * ry);
+            atomicAdd(a + 3, (unsigned long long)sx);
+            k = 0; sx = 0;
+        }
+        if (valid) {
+            if (!k) { run_id = id; ry = py; rz = pz; }
+            ++k;
+            sx += px;
+        }
+        if (++px >= nx) { px = 0; if (++py >= ny) { py = 0; ++pz; } }
+    }
+    if (k) {
+        unsigned long long *a = acc + (size_t)run_id * 4;
+        atomicAdd(a + 0, (unsigned long long)k);
+        atomicAdd(a + 1, (unsigned long long)k * rz);
+        atomicAdd(a + 2, (unsigned long long)k * ry);
+        atomicAdd(a + 3, (unsigned long long)sx);
+    }
+}
+
+#define PM_LABEL_STREAM_UNROLL 8      // independent 16-byte loads in flight per thread (128 B)
+
+// labels must be 16-byte aligned; the voxels beyond the last full chunk are handled by thread 0 of block 0
+template <typename T>
+__global__ void __launch_bounds__(256, 4) pm_label_stream_kernel(const T *__restrict__ labels, int nz, int ny, int nx,
+                                                              unsigned table_size, unsigned long long *__restrict__ acc) {
+    constexpr int VPC = 16 / (int)sizeof(T);
+    const size_t n_vox = (size_t)nz * ny * nx;
+    const size_t n_chunks = n_vox / VPC;
+    const unsigned plane = (unsigned)ny * (unsigned)nx;          // (ny, nx < 2^26 and the host checks ny * nx < 2^32)
+    const uint4 *__restrict__ p = reinterpret_cast<const uint4 *>(labels);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += stride * PM_LABEL_STREAM_UNROLL) {
+        uint4 q[PM_LABEL_STREAM_UNROLL];
+#pragma unroll
+        for (int u = 0; u < PM_LABEL_STREAM_UNROLL; ++u) {
+            const size_t idx = c + (size_t)u * stride;
+            q[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (idx < n_chunks) q[u] = __ldcs(p + idx);            // streamed once: evict first
+        }
+#pragma unroll
+        for (int u = 0; u < PM_LABEL_STREAM_UNROLL; ++u)
+            if ((q[u].x | q[u].y | q[u].z | q[u].w) != 0u)
+                pm_label_chunk<T>(q[u], (c + (size_t)u * stride) * VPC, plane, (unsigned)ny, (unsigned)nx, table_size, acc);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (size_t v = n_chunks * VPC; v < n_vox; ++v) {         // < VPC voxels
+            const int id = (int)labels[v];
+            if (id > 0 && (unsigned)id < table_size) {
+                const unsigned pz = (unsigned)(v / plane), rem = (unsigned)(v - (size_t)pz * plane);
+                unsigned long long *a = acc + (size_t)id * 4;
+                atomicAdd(a + 0, 1ull);
+                atomicAdd(a + 1, (unsigned long long)pz);
+                atomicAdd(a + 2, (unsigned long long)(rem / nx));
+                atomicAdd(a + 3, (unsigned long long)(rem % nx));
+            }
+        }
+    }
+}
+
 // one CTA: ids with a non-zero count, ascending, -> ids / centroids (z, y, x) / sizes
 __global__ void __launch_bounds__(1024) pm_label_finalize_kernel(const unsigned long long *__restrict__ acc,
                                                                  unsigned table_size, double anisotropy, int capacity,
@@ -207,7 +301,17 @@ static int pm_label_run(const T *labels, int nz, int ny, int nx, unsigned table_
     PM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     size_t want = (n_vox + 1023) / 1024;
     const int blocks = (int)(want < (size_t)sms * 8 ? (want ? want : 1) : (size_t)sms * 8);   // 8 resident CTAs per SM
-    pm_label_accumulate_kernel<T><<<blocks, 256, 0, s>>>(labels, nz, ny, nx, table_size, acc);
+    const bool stream_ok = (reinterpret_cast<size_t>(labels) & 15) == 0 && (size_t)ny * nx < ((size_t)1 << 32) &&
+                           !getenv("PM_LABEL_WARP_KERNEL");
+    if (stream_ok) {
+        // 128 B per thread in flight; a grid of whole waves (8 CTAs of 256 threads per SM)
+        const size_t chunks = n_vox / (16 / sizeof(T));
+        size_t want2 = (chunks + 256 * PM_LABEL_STREAM_UNROLL - 1) / (256 * PM_LABEL_STREAM_UNROLL);
+        const int blocks2 = (int)(want2 < (size_t)sms * 8 ? (want2 ? want2 : 1) : (size_t)sms * 8);
+        pm_label_stream_kernel<T><<<blocks2, 256, 0, s>>>(labels, nz, ny, nx, table_size, acc);
+    } else {
+        pm_label_accumulate_kernel<T><<<blocks, 256, 0, s>>>(labels, nz, ny, nx, table_size, acc);
+    }
     PM_LAUNCH_CHECK();
     pm_label_finalize_kernel<<<1, 1024, 0, s>>>(acc, table_size, anisotropy, capacity, ids, centroids, sizes, n_out);
     PM_LAUNCH_CHECK();

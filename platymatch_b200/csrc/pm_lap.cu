@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(256) pm_ls_bulk_kernel(PmLapBatch B, int ctas_
             int result = PM_LS_RETRY;
             unsigned prev = 0xFFFFFFFFu;
             if (holder) {
-                if (gamma == 0.0 && own != 0xFFFFFFFFu) result = PM_LS_PARK;            // zero-increment steal
+                if (v1 - gamma == v1 && own != 0xFFFFFFFFu) result = PM_LS_PARK;        // zero-increment steal (or an increment below the price's resolution)
                 else if (pm_ls_cas128(&cell[bj], v1, own, v1 - gamma, (unsigned)row)) {
                     result = PM_LS_WON;
                     if (own != 0xFFFFFFFFu) {
@@ -915,7 +915,7 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
                 const double vj = *reinterpret_cast<volatile double *>(&v[bj]);
                 if (vj != v1) {
                     *reinterpret_cast<volatile unsigned short *>(p) = old;                 // price moved: recompute
-                } else if (gamma == 0.0 && old != PM_LS_NONE) {
+                } else if (vj - gamma == vj && old != PM_LS_NONE) {
                     *reinterpret_cast<volatile unsigned short *>(p) = old;                 // zero-increment steal: park
                     result = PM_LS_PARK;
                 } else {

@@ -309,25 +309,41 @@ class PeerWindow:
         torch = _torch()
         self.nbytes, self.group = int(nbytes), group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        p = ctypes.c_void_p()
-        check(load().pm_peer_alloc(self.nbytes, ctypes.byref(p)), "pm_peer_alloc")
-        self.ptr = p.value
+        self.ptr, self.remote, self._opened = None, [], []
+        # every step that can fail is followed by a collective in which ALL ranks learn about it and raise together
         handle = (ctypes.c_ubyte * 64)()
-        check(load().pm_peer_export(ctypes.c_void_p(self.ptr), handle), "pm_peer_export")
-        mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
-        everyone = torch.empty((self.world, 64), dtype=torch.uint8, device="cuda")
+        err = None
+        try:
+            p = ctypes.c_void_p()
+            check(load().pm_peer_alloc(self.nbytes, ctypes.byref(p)), "pm_peer_alloc")
+            self.ptr = p.value
+            check(load().pm_peer_export(ctypes.c_void_p(self.ptr), handle), "pm_peer_export")
+        except Exception as e:
+            err = e
+        mine = torch.tensor(list(handle) + [0 if err is None else 1], dtype=torch.uint8, device="cuda")
+        everyone = torch.empty((self.world, 65), dtype=torch.uint8, device="cuda")
         dist.all_gather_into_tensor(everyone, mine, group=group)
         handles = everyone.cpu().numpy()
-        self.remote, self._opened = [], []
+        if handles[:, 64].any():
+            self.close()
+            raise _lib.PlatyMatchError("peer window: allocation / export failed on a rank (%s)" % (err,))
         for r in range(self.world):
             if r == self.rank:
                 self.remote.append(self.ptr)
                 continue
             q = ctypes.c_void_p()
-            buf = (ctypes.c_ubyte * 64)(*handles[r].tolist())
-            check(load().pm_peer_open(buf, ctypes.byref(q)), "pm_peer_open")
+            buf = (ctypes.c_ubyte * 64)(*handles[r, :64].tolist())
+            try:
+                check(load().pm_peer_open(buf, ctypes.byref(q)), "pm_peer_open")
+                self._opened.append(q.value)
+            except Exception as e:
+                err = e
             self.remote.append(q.value)
-            self._opened.append(q.value)
+        flag = torch.tensor([0 if err is None else 1], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        if int(flag.item()):
+            self.close()
+            raise _lib.PlatyMatchError("peer window: cudaIpcOpenMemHandle failed on a rank (%s)" % (err,))
 
     def tensor(self, shape, dtype, offset_bytes=0):
         """A torch view of (part of) the local buffer."""

@@ -230,17 +230,40 @@ def describe_cloud_sharded(cloud, n_variants, group=None, transposed=False):
 
 
 _WINDOWS = {}
+_PEER_BROKEN = set()
 
 
 def _cost_window(nbytes, group=None):
-    """This rank's peer-mapped cost-matrix window (grown on demand, reused across registrations).  Collective."""
+    """This rank's peer-mapped cost-matrix window (grown on demand, reused across registrations), or None when CUDA IPC
+    is not available between the ranks (then every later call goes through dist.gather).  Collective: all ranks
+    decide together."""
+    import torch
+    import torch.distributed as dist
     from . import device as D
     key = id(group)
+    if key in _PEER_BROKEN:
+        return None
     win = _WINDOWS.get(key)
-    if win is None or win.nbytes < nbytes:
+    if win is not None and win.nbytes >= nbytes:
+        return win
+    if win is not None:
+        win.close()
+        del _WINDOWS[key]
+    err = None
+    try:
+        win = D.PeerWindow(nbytes, group)
+    except Exception as e:          # e.g. IPC disabled in the container
+        err, win = e, None
+    flag = torch.tensor([0 if err is None else 1], dtype=torch.int32, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    if int(flag.item()):
         if win is not None:
             win.close()
-        win = _WINDOWS[key] = D.PeerWindow(nbytes, group)
+        _PEER_BROKEN.add(key)
+        import warnings
+        warnings.warn("platymatch_b200: peer-mapped windows unavailable (%s); cost rows go through dist.gather" % (err,))
+        return None
+    _WINDOWS[key] = win
     return win
 
 
@@ -300,9 +323,14 @@ def register_pair_sharded(moving, fixed, *, ransac_samples=4, ransac_trials=8000
     if world == 1:
         for q, (a, b) in enumerate(hyps):
             costs[q] = D.chi2_cost(dm.operand(a), df.operand(b))
-    elif peer_stores:
+    win = None
+    if world > 1 and peer_stores:
         slots = max(1, -(-H // world))
         win = _cost_window(slots * n1 * ldc * 4, group)             # collective (first call / growth only)
+        peer_stores = win is not None
+    if world == 1:
+        pass
+    elif peer_stores:
         for q in mine:
             costs[q] = win.tensor((n1, ldc), torch.float32, offset_bytes=mine.index(q) * n1 * ldc * 4)
         dist.barrier(group)                                          # the owners' previous matrices are no longer in use

@@ -25,6 +25,15 @@ def linear_sum_assignment(cost_matrix, maximize=False, return_stats=False, max_b
         raise ValueError("matrix contains invalid numeric entries")
     if maximize:
         c = -c
+    if c.dtype != np.float32 and c.size <= (1 << 22):
+        # the kernel solves the float32 image of the matrix (exactly); say so when that image merges distinct costs
+        # (integer costs above 2^24, huge dynamic range), because scipy's float64 optimum can then be a different one
+        c32 = c.astype(np.float32)
+        if np.unique(c32).size < np.unique(c).size and not np.array_equal(c32.astype(np.float64), c):
+            import warnings
+            warnings.warn("linear_sum_assignment: float32 rounding merges distinct cost values; the result is optimal "
+                          "for the rounded matrix and may differ from a float64 solve near ties", RuntimeWarning,
+                          stacklevel=2)
     transposed = c.shape[0] > c.shape[1]
     if transposed:
         c = c.T

@@ -126,3 +126,27 @@ def test_chi2_filled_cloud_dense_histograms(O, torch, n):
         U = O.unary_distance_matrix(O.normalise_counts(om), O.normalise_counts(of))
         G = D.chi2_cost(dm.operand(1), df.operand(b))[:, :f.shape[1]].cpu().numpy()
         assert float((np.abs(G - U) / U).max()) < 1e-5
+
+
+def test_config4_20k_assignment_exact_single_gpu(O, torch):
+    """BASELINE config 4 size on ONE GPU (18000 x 20000): the assignment of the true hypothesis' matrix has the
+    oracle's optimal cost and the identical assignment (the oracle's C shortest-augmenting-path solve of the same
+    float32 values: the expensive half of this test), and the registration recovers the ground truth."""
+    from platymatch_b200 import pipeline as P
+    from platymatch_b200.synthetic import make_pair
+    p = make_pair(20000, seed=2)
+    dm, df = P.describe_pair(p["moving"], p["fixed"], 1, 4)
+    res = P.register_described(dm, df, seed=1, keep_cost=True)       # device results: only ONE 1.44 GB matrix comes back
+    inliers = res["inliers"].cpu().numpy()
+    best = int(res["best"].item())
+    n1 = p["moving"].shape[1]
+    assert n1 == 18000 and inliers[best] > 3 * np.delete(inliers, best).max()
+    T = res["transform"].cpu().numpy().reshape(4, 4)
+    moved = O.apply_affine_transform(p["moving"], T)
+    assert np.median(np.linalg.norm(moved - p["fixed"][:, p["gt_fixed_index"]], axis=0)) < 4.0
+    G = res["cost"][best][:, :20000].cpu().numpy().astype(np.float64)
+    got = res["assignments"][best][1].cpu().numpy()
+    assert len(np.unique(got)) == n1
+    ro, co = O.linear_sum_assignment(G)
+    assert res["lap_cost"][best].item() == pytest.approx(G[ro, co].sum(), rel=1e-12)
+    assert np.array_equal(got, co), int((got != co).sum())

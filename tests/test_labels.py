@@ -77,6 +77,22 @@ def test_detections_from_labels_bit_exact(shape, n, dtype, sparse):
 
 
 @pytest.mark.gpu
+def test_label_kernels_agree(monkeypatch):
+    """The round-2 streaming kernel (per-thread run-length items) and the round-1 warp-cooperative kernel (kept for
+    unaligned volumes, PM_LABEL_WARP_KERNEL=1) produce identical tables on a crowded volume with touching nuclei."""
+    from platymatch_b200.synthetic import make_label_volume
+    from platymatch_b200.utils.labels import detections_from_labels
+    for shape, dtype in (((70, 83, 101), np.int32), ((70, 83, 101), np.uint16), ((16, 16, 1030), np.int32)):
+        vol = make_label_volume(shape, 500, radius=(2.0, 7.0), seed=4, dtype=dtype)
+        a = detections_from_labels(vol)
+        monkeypatch.setenv("PM_LABEL_WARP_KERNEL", "1")
+        b = detections_from_labels(vol)
+        monkeypatch.delenv("PM_LABEL_WARP_KERNEL")
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+
+
+@pytest.mark.gpu
 def test_detections_from_labels_int64_and_negative_background():
     import oracle as O
     from platymatch_b200.utils.labels import detections_from_labels
