@@ -38,6 +38,14 @@ METRIC = "registrations/sec"
 CHI2_NCU_DRAM_BYTES = 186.0e6     # measured once with ncu at the headline size (10.6 MB read + 175.4 MB written)
 
 
+def workload_config(n1, n2, trials):
+    """`config` of the JSON line: the workload, identical keys and values in both arms (b200 and reference)."""
+    return {"workload": WORKLOAD, "n_fixed": int(n2), "n_moving": int(n1), "hypotheses": 4, "ransac_trials": int(trials),
+            "icp_iterations": ICP_ITERS,
+            "l2": "inputs larger than L2: 4 x %.0f MB cost matrices rewritten every step (> 126 MB L2); 4 input pairs cycled"
+                  % (n1 * n2 * 4 / 1e6)}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -204,8 +212,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "registrations/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_fixed": args.n_fixed, "ransac_trials": args.trials,
-                       "icp_iterations": ICP_ITERS, "hypotheses": 4},
+            "config": workload_config(arm.n1, arm.n2, args.trials),
             "cpu_baseline": cb,
             "e2e": {"value": val, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -240,7 +247,7 @@ def bench_label_row(torch, D, hbm_peak, with_cpu):
     out = {"workload": "label volume %dx%dx%d int32, %d nuclei (%.0f %% foreground)" %
                        (shape + (int(ids.numel()), 100.0 * float((vol > 0).mean()))),
            "ms": ms, "voxels_per_s": vol.size / (ms * 1e-3),
-           "roofline": {"kernel": "pm_label_accumulate_kernel", "bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9,
+           "roofline": {"kernel": "pm_label_stream_kernel (+ memset of the table + pm_label_finalize_kernel inside the timed region)", "bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9,
                         "peak": hbm_peak, "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak, "of": "measured",
                         "algorithmic_bytes": nbytes, "l2": "160 MB flush between repetitions"}}
     if with_cpu:
@@ -410,18 +417,19 @@ def bench_sharded_20k(torch, dist, world, rank, args):
             "inliers": [int(x) for x in res["inliers"]], "median_error_px": err, "recovered": bool(err < 4.0)}
 
 
-def bench_allpairs(torch, dist, world, rank, args):
-    """BASELINE config 5: 12 specimens (~8k nuclei each, sizes differ by up to 5 %), all 66 pairs, pulled from one
-    shared work counter by 3 in-flight registrations per GPU."""
+def bench_allpairs(torch, dist, world, rank, args, vary=0.05, runs=2):
+    """BASELINE config 5: 12 specimens (~8k nuclei each; sizes differ by up to 5 %, or EXACTLY equal with vary=0: every
+    assignment then is a problem without slack columns), all 66 pairs, pulled from one shared work counter by 3
+    in-flight registrations per GPU."""
     from platymatch_b200 import distributed as PD
     from platymatch_b200.synthetic import make_specimens
     n = args.n_fixed
-    specs = make_specimens(12, n, seed=0)
+    specs = make_specimens(12, n, seed=0, vary=vary)
     clouds = [sp["points"] for sp in specs]
     kw = dict(ransac_trials=args.trials, icp_iterations=ICP_ITERS)
     PD.register_all_pairs(clouds[:4], in_flight=3, **kw)                # warm-up (6 pairs)
     best, st_best = None, None
-    for _ in range(2):
+    for _ in range(runs):
         st = {}
         torch.cuda.synchronize()
         if world > 1:
@@ -451,7 +459,7 @@ def bench_allpairs(torch, dist, world, rank, args):
                         % ("%d-%d" % (min(c.shape[1] for c in clouds), max(c.shape[1] for c in clouds)), len(pairs), world),
             "seconds": dt, "pairs_per_s": len(pairs) / dt, "recovered": int(ok), "pairs": len(pairs),
             "timing": "host clock around register_all_pairs with HOST inputs (descriptors of the 12 specimens, H2D and the "
-                      "result gather inside), barrier + synchronize on both sides, max over ranks, best of 2",
+                      "result gather inside), barrier + synchronize on both sides, max over ranks, best of %d" % runs,
             "pairs_per_rank": [int(x) for x in per_rank[:, 0]], "busy_s_per_rank": [float(x) for x in per_rank[:, 1]]}
 
 
@@ -460,7 +468,7 @@ def bench_square(torch, args):
     case for auctions)."""
     import platymatch_b200 as pm
     from platymatch_b200.synthetic import make_pair
-    p = make_pair(args.n_fixed, seed=args.n_fixed + 5, dropout=0.0)
+    p = make_pair(args.n_fixed, seed=args.n_fixed + 11, dropout=0.0)
     kw = dict(ransac_trials=args.trials, icp_iterations=ICP_ITERS)
     pm.estimate_transform_unsupervised(p["moving"], p["fixed"], seed=1, **kw)
     ms = []
@@ -663,7 +671,8 @@ def run_b200(args):
     rows = {}
     if not args.no_rows:
         torch.cuda.empty_cache()
-        for name, fn in (("sharded_20k", bench_sharded_20k), ("allpairs_66", bench_allpairs)):
+        for name, fn in (("sharded_20k", bench_sharded_20k), ("allpairs_66", bench_allpairs),
+                         ("allpairs_66_equal_sizes", lambda *a: bench_allpairs(*a, vary=0.0, runs=1))):
             try:
                 rows[name] = fn(torch, dist, world, rank, args)
             except Exception as e:          # a secondary row must not take the headline down with it
@@ -683,10 +692,10 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": "registrations/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64 descriptors/duals/transforms, f32 cost matrix", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_fixed": n2, "n_moving": n1, "hypotheses": 4, "ransac_trials": args.trials,
-                   "icp_iterations": ICP_ITERS, "lap_bid_rounds": bid_rounds, "parallelism": "pairs sharded, 1 rank/GPU",
-                   "l2": "4 x %.0f MB cost matrices rewritten every step (> 126 MB L2); 4 input pairs cycled" %
-                         (n1 * n2 * 4 / 1e6)},
+        "config": workload_config(n1, n2, args.trials),
+        "impl_config": {"lap_bid_rounds": bid_rounds, "parallelism": "pairs sharded, 1 rank/GPU",
+                        "l2": "4 x %.0f MB cost matrices rewritten every step (> 126 MB L2); 4 input pairs cycled" %
+                              (n1 * n2 * 4 / 1e6)},
         "e2e": {"value": e2e_val, "unit": "registrations/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": e2e_bytes.get("h2d"), "d2h_bytes_per_step": e2e_bytes.get("d2h"),
                 "api": "platymatch_b200.estimate_transform_unsupervised(numpy 3xN, numpy 3xN) -> dict of numpy arrays: "

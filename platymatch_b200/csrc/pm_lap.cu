@@ -30,6 +30,8 @@
 
 namespace cg = cooperative_groups;
 
+// squared (dummy rows + eps-scaling) when nc - nr <= this fraction of nc; measured crossover at 8k, profiles/r2_lap_slack.txt
+#define PM_LAP_SQUARE_SLACK_DEFAULT 0.015
 #define PM_LAP_BID_THREADS 1024
 #define PM_LAP_CPT 8
 #define PM_LAP_MAX_THREADS 1024
@@ -569,11 +571,52 @@ __device__ __forceinline__ int pm_ls_refresh_row(const PmLapView &V, int row, co
     __syncwarp();
     cj = __ldcg(reinterpret_cast<const int4 *>(lcol) + lane);
     cc = __ldcg(reinterpret_cast<const float4 *>(lcost) + lane);
-    return count < PM_LS_K ? count : PM_LS_K;
+    return count;          // columns below the limit (more than PM_LS_K: the surplus was dropped and lowered tau)
+}
+
+// Rebuild a row's list so that it CERTIFIES its own best entry again (one warp).  First the window the previous list
+// covered above the old bound; if that catches fewer than 8 columns (prices moved a lot) a 4x wider one centred on the
+// row minimum.  The slots fill in COLUMN order, so when more than PM_LS_K columns lie below the limit the row minimum
+// itself can be among the dropped ones: then tau <= wmin, the list certifies nothing, and repeating the same two
+// windows would never end (a matrix of ones with one zero per row after a price drop; the near-ties of an
+// eps-equilibrium).  The window above the minimum therefore shrinks by the overflow ratio until the minimum is inside
+// (at most PM_LS_K columns below the limit, or only exact ties at the minimum left: tau == wmin, a zero increment).
+template <bool CELLS>
+__device__ __forceinline__ void pm_ls_refresh_certified(const PmLapView &V, const PmLapBatch &B, int row, const double *prices,
+                                                        int nc, int lane, int4 &cj, float4 &cc, double &tau) {
+    double width = __ldcg(V.width + row), wmin;
+    if (!(width > 0.0) || !(width < INFINITY)) width = fabs(tau) * 1e-3 + 1e-300;
+    const float *ci = pm_lap_row(V.cost, B, row);
+    double limit = tau + width;
+    int n = pm_ls_refresh_row<CELLS>(V, row, ci, prices, nc, lane, limit, cj, cc, tau, wmin);
+    if (n < 8 && wmin < INFINITY) {            // window too narrow (prices moved a lot): centre it on the minimum
+        width *= 4.0;
+        limit = wmin + width;
+        if (!(limit > wmin)) limit = nextafter(wmin, (double)INFINITY);
+        n = pm_ls_refresh_row<CELLS>(V, row, ci, prices, nc, lane, limit, cj, cc, tau, wmin);
+    } else if (n >= PM_LS_K) {
+        width *= 0.5;
+    }
+    for (int guard = 0; n > PM_LS_K && !(wmin < tau) && wmin < INFINITY && guard < 128; ++guard) {
+        double span = limit - wmin, next;
+        if (span > 0.0 && span < INFINITY) {
+            next = wmin + span * (0.5 * (double)PM_LS_K / (double)n);
+            if (!(next > wmin)) next = nextafter(wmin, (double)INFINITY);
+            if (!(next < limit)) break;                               // only exact ties at the minimum are left
+        } else {
+            next = wmin + width;                                      // (prices fell meanwhile: the minimum moved past the limit)
+            if (!(next > wmin)) next = nextafter(wmin, (double)INFINITY);
+        }
+        limit = next;
+        n = pm_ls_refresh_row<CELLS>(V, row, ci, prices, nc, lane, limit, cj, cc, tau, wmin);
+        if (limit - wmin > 0.0) width = limit - wmin;
+    }
+    if (lane == 0) { V.tau[row] = tau; V.width[row] = width; }
 }
 
 
 enum { PM_LS_WON = 0, PM_LS_PARK = 1, PM_LS_RETRY = 2 };
+#define PM_LS_MAX_SPINS 4096   // recomputations (lost races, list rebuilds) of ONE bid before the row is left to phase 2
 
 // ---- bulk phase: the same certified bids, spread over many SMs --------------------------------------
 // While thousands of rows are free the auction is throughput-bound, so the bulk of the bids runs on
@@ -599,7 +642,7 @@ __device__ __forceinline__ bool pm_ls_cas128(PmLsCell *addr, double exp_price, u
 
 __global__ void __launch_bounds__(256) pm_ls_bulk_kernel(PmLapBatch B, int ctas_per_matrix) {
     const PmLapView V = pm_lap_view(B, blockIdx.x / ctas_per_matrix);
-    const int nr = B.nr, nc = B.nc, lane = threadIdx.x & 31;
+    const int nr = B.nr_real, nc = B.nc, lane = threadIdx.x & 31;
     PmLsCell *cell = V.cell;
     volatile unsigned *ring = V.ring32;
     const unsigned ring_mask = B.ring_cap - 1;
@@ -634,33 +677,20 @@ __global__ void __launch_bounds__(256) pm_ls_bulk_kernel(PmLapBatch B, int ctas_
             row = __shfl_sync(0xffffffffu, row, 0);
             if (row < 0) break;
         }
-        // A DUMMY row (row >= nr_real: all costs zero, present when a problem with few slack columns was made
-        // square) has no use for a candidate list: its reduced values are just the negated prices, so it bids
-        // from one sweep over the price cells (exact best / second best, no certificate needed).
-        const bool dummy = row >= B.nr_real;
-        int4 cj = make_int4(-1, -1, -1, -1);
-        float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
-        double tau = INFINITY;
-        if (!dummy) {
-            cj = __ldcg(reinterpret_cast<const int4 *>(V.lcol + (size_t)row * PM_LS_K) + lane);
-            cc = __ldcg(reinterpret_cast<const float4 *>(V.lcost + (size_t)row * PM_LS_K) + lane);
-            tau = __ldcg(V.tau + row);
-        }
+        // (DUMMY rows, row >= nr_real, present when a problem with few slack columns was made square, never bid here:
+        // a dummy's bid is a sweep over all prices, cheap in the tail kernel's shared memory and ~40 us through L2;
+        // a displaced dummy is simply left free and the tail kernel seats it)
+        int4 cj = __ldcg(reinterpret_cast<const int4 *>(V.lcol + (size_t)row * PM_LS_K) + lane);
+        float4 cc = __ldcg(reinterpret_cast<const float4 *>(V.lcost + (size_t)row * PM_LS_K) + lane);
+        double tau = __ldcg(V.tau + row);
         bool fresh = false, won = false;
+        int spins = 0;
         while (true) {
+            if (++spins > PM_LS_MAX_SPINS) break;           // watchdog: the row stays free for the augmenting paths
             double w1, w2, v1 = 0.0;        // lane-local: best and second-best reduced value, price / owner of the best
             int bj = -1;
             unsigned own = 0xFFFFFFFFu;
-            if (dummy) {
-                w1 = INFINITY; w2 = INFINITY;
-#pragma unroll 4
-                for (int j = lane; j < nc; j += 32) {
-                    const ulonglong2 c = __ldcv(reinterpret_cast<const ulonglong2 *>(&cell[j]));
-                    const double vj = __longlong_as_double((long long)c.x), w = -vj;
-                    if (w < w1) { w2 = w1; w1 = w; bj = j; v1 = vj; own = (unsigned)c.y; }
-                    else if (w < w2) w2 = w;
-                }
-            } else {
+            {
                 const int js[4] = {cj.x, cj.y, cj.z, cj.w};
                 const float cs[4] = {cc.x, cc.y, cc.z, cc.w};
                 double vs[4], ws[4];
@@ -690,18 +720,7 @@ __global__ void __launch_bounds__(256) pm_ls_bulk_kernel(PmLapBatch B, int ctas_
             const double sw = pm_ordval(pm_warp_min_u64(pm_ordkey(holder ? w2 : w1)));
             if (!(bw < INFINITY)) break;                    // no finite entry: phase 2 reports it
             if (!(bw < tau) && !(fresh && bw <= tau)) {     // list exhausted: rebuild from the dense row
-                double width = __ldcg(V.width + row), wmin;
-                if (!(width > 0.0) || !(width < INFINITY)) width = fabs(tau) * 1e-3 + 1e-300;
-                const float *ci = pm_lap_row(V.cost, B, row);
-                const double *prices = reinterpret_cast<const double *>(cell);
-                int n = pm_ls_refresh_row<true>(V, row, ci, prices, nc, lane, tau + width, cj, cc, tau, wmin);
-                if (n < 8 && wmin < INFINITY) {
-                    width *= 4.0;
-                    n = pm_ls_refresh_row<true>(V, row, ci, prices, nc, lane, wmin + width, cj, cc, tau, wmin);
-                } else if (n >= PM_LS_K) {
-                    width *= 0.5;
-                }
-                if (lane == 0) { V.tau[row] = tau; V.width[row] = width; }
+                pm_ls_refresh_certified<true>(V, B, row, reinterpret_cast<const double *>(cell), nc, lane, cj, cc, tau);
                 __threadfence();                            // the next warp that serves this row may sit on another SM
                 fresh = true;
                 ++refreshes;
@@ -716,7 +735,7 @@ __global__ void __launch_bounds__(256) pm_ls_bulk_kernel(PmLapBatch B, int ctas_
                 if (v1 - gamma == v1 && own != 0xFFFFFFFFu) result = PM_LS_PARK;        // zero-increment steal (or an increment below the price's resolution)
                 else if (pm_ls_cas128(&cell[bj], v1, own, v1 - gamma, (unsigned)row)) {
                     result = PM_LS_WON;
-                    if (own != 0xFFFFFFFFu) {
+                    if (own != 0xFFFFFFFFu && (int)own < nr) {
                         // displaced owner: behind everything that is queued, or carried on by this warp
                         const bool queued = ctr[PM_LS_CTR_FRESH] < nr ||
                                             (int)((unsigned)ctr[PM_LS_CTR_TAIL] - (unsigned)ctr[PM_LS_CTR_HEAD]) > 0;
@@ -751,6 +770,7 @@ struct PmLsShared {
     int fresh;              // next fresh row
     unsigned head, tail;    // ring of displaced rows
     int live;               // warps still bidding
+    int dummy_token;        // held by the one warp that bids for a dummy row (see the tail kernel)
     unsigned long long stat[6];   // bids, refreshes, retries, parked, refresh cycles, (max) busy cycles
     unsigned long long maxbids;
 };
@@ -777,7 +797,7 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
     for (unsigned q = t; q < B.ring_cap; q += blockDim.x) ring[q] = PM_LS_EMPTY;
     for (int i = t; i < nr; i += blockDim.x) { V.col4row[i] = -1; V.u[i] = 0.0; }
     if (t == 0) {
-        S.fresh = nr; S.head = 0; S.tail = 0; S.maxbids = 0; S.live = blockDim.x >> 5;
+        S.fresh = nr; S.head = 0; S.tail = 0; S.maxbids = 0; S.live = blockDim.x >> 5; S.dummy_token = 0;
         for (int k = 0; k < 6; ++k) S.stat[k] = 0;
     }
     __syncthreads();
@@ -803,6 +823,7 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
     }
     const double eps = pm_ls_eps(B, blockIdx.x);
     long long bids = 0, refreshes = 0, retries = 0, parked = 0, refresh_cycles = 0;
+    int requeues = 0;
     const long long t_begin = clock64();
     int carry = -1;          // displaced owner this warp continues with (only when nothing is queued)
     while (bids < B.max_bids_tail) {
@@ -831,7 +852,28 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
             row = __shfl_sync(0xffffffffu, row, 0);
             if (row < 0) break;
         }
-        const bool dummy = row >= B.nr_real;          // zero-cost row: bids from one sweep over the prices (see the bulk kernel)
+        // A DUMMY row (row >= nr_real: all costs zero, present when a problem with few slack columns was made square) has
+        // no use for a candidate list: its reduced values are just the negated prices, so it bids from one sweep over the
+        // prices (exact best / second best, no certificate needed).  All dummies want the same column, the most expensive
+        // one: bidding for them concurrently means that every commit invalidates the sweeps of all the others (measured:
+        // ~2 ms per dummy and solve at 8k).  ONE warp at a time bids for a dummy; the others put theirs back in the queue.
+        const bool dummy = row >= B.nr_real;
+        if (dummy) {
+            int got = 0;
+            if (lane == 0) {
+                got = atomicCAS(&S.dummy_token, 0, 1) == 0;
+                if (!got) {
+                    const unsigned pos = atomicAdd(&S.tail, 1u);
+                    ring[pos & ring_mask] = (unsigned short)row;
+                }
+            }
+            got = __shfl_sync(0xffffffffu, got, 0);
+            if (!got) {
+                if (++requeues > (1 << 22)) break;       // (watchdog; the token holder always finishes its bid)
+                __nanosleep(400);
+                continue;
+            }
+        }
         int4 cj = make_int4(-1, -1, -1, -1);
         float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
         double tau = INFINITY;
@@ -841,15 +883,25 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
             tau = __ldcg(V.tau + row);
         }
         bool fresh = false;
-        int result, prev = PM_LS_NONE;
+        int result, prev = PM_LS_NONE, spins = 0;
         while (true) {
+            if (++spins > PM_LS_MAX_SPINS) { result = PM_LS_PARK; break; }        // watchdog: left to the augmenting paths
             double w1, w2, v1 = 0.0;        // lane-local: best and second-best reduced value, price of the best
             int bj = -1;
             if (dummy) {
+                // eps-scaling phases: the dummies bid as ONE class of similar persons (Bertsekas & Castanon): a dummy
+                // looks only at columns that no other dummy holds.  Bidding individually, a displaced dummy takes the
+                // most expensive column from the next dummy, which takes the next one ... a chain through all
+                // nc - nr dummies for every column a real row takes from them (measured: 2.3 ms per dummy and solve
+                // at 8k).  The class keeps eps-complementary-slackness as a whole (every column outside it costs at
+                // most the cheapest dummy-held column + eps).  The exact phase (eps = 0) bids individually: there the
+                // dummies sit on equal prices (pm_ls_equalise_dummies_kernel) and a displaced one parks at once.
                 w1 = INFINITY; w2 = INFINITY;
 #pragma unroll 4
                 for (int j = lane; j < nc; j += 32) {
                     const double vj = *reinterpret_cast<volatile double *>(&v[j]), w = -vj;
+                    const unsigned short oj = *reinterpret_cast<volatile unsigned short *>(&owner[j]);
+                    if (eps > 0.0 && oj < PM_LS_LOCKED && (int)oj >= B.nr_real) continue;
                     if (w < w1) { w2 = w1; w1 = w; bj = j; v1 = vj; }
                     else if (w < w2) w2 = w;
                 }
@@ -886,23 +938,14 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
             if (!(bw < tau) && !(fresh && bw <= tau)) {
                 // list exhausted: cannot certify the best column -> rebuild from the dense row
                 const long long t0 = clock64();
-                double width = __ldcg(V.width + row), wmin;
-                if (!(width > 0.0) || !(width < INFINITY)) width = fabs(tau) * 1e-3 + 1e-300;
-                int n = pm_ls_refresh_row<false>(V, row, pm_lap_row(V.cost, B, row), v, nc, lane, tau + width, cj, cc, tau, wmin);
-                if (n < 8 && wmin < INFINITY) {        // window too narrow (prices moved a lot): centre it on the minimum
-                    width *= 4.0;
-                    n = pm_ls_refresh_row<false>(V, row, pm_lap_row(V.cost, B, row), v, nc, lane, wmin + width, cj, cc, tau, wmin);
-                } else if (n >= PM_LS_K) {
-                    width *= 0.5;
-                }
-                if (lane == 0) { V.tau[row] = tau; V.width[row] = width; }
+                pm_ls_refresh_certified<false>(V, B, row, v, nc, lane, cj, cc, tau);
                 fresh = true;
                 ++refreshes;
                 refresh_cycles += clock64() - t0;
                 continue;
             }
             double gamma = fmin(sw, tau) - bw;    // certified lower bound of the true increment
-            if (!(gamma > 0.0)) gamma = 0.0;
+            if (!(gamma > 0.0) || !(gamma < INFINITY)) gamma = 0.0;       // (infinite: a dummy with one column to choose from)
             gamma += eps;                         // (eps-scaling phases; 0 in the exact phases)
             result = PM_LS_RETRY;
             if (holder) {
@@ -913,8 +956,8 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
                     if (old != PM_LS_LOCKED && atomicCAS(p, old, (unsigned short)PM_LS_LOCKED) == old) break;
                 }
                 const double vj = *reinterpret_cast<volatile double *>(&v[bj]);
-                if (vj != v1) {
-                    *reinterpret_cast<volatile unsigned short *>(p) = old;                 // price moved: recompute
+                if (vj != v1 || (dummy && eps > 0.0 && old < PM_LS_LOCKED && (int)old >= B.nr_real)) {
+                    *reinterpret_cast<volatile unsigned short *>(p) = old;                 // price moved (or another dummy took it): recompute
                 } else if (vj - gamma == vj && old != PM_LS_NONE) {
                     *reinterpret_cast<volatile unsigned short *>(p) = old;                 // zero-increment steal: park
                     result = PM_LS_PARK;
@@ -941,6 +984,10 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
             prev = __shfl_sync(0xffffffffu, prev, hl);
             if (result != PM_LS_RETRY) break;
             ++retries;
+        }
+        if (dummy) {
+            __threadfence_block();
+            if (lane == 0) atomicExch(&S.dummy_token, 0);
         }
         ++bids;
         if (result == PM_LS_PARK) ++parked;
@@ -1463,7 +1510,7 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
     // (see below).  The dummies take the columns that stay unassigned, so the optimum over the real rows is the same.
     bool square = false;
     if (max_bid_rounds > 0 && algorithm != PM_LAP_ALGO_DENSE_AUCTION && nr >= 64) {
-        double max_slack = 0.08;                              // of nc; above it the pure epsilon = 0 schedule is faster
+        double max_slack = PM_LAP_SQUARE_SLACK_DEFAULT;        // of nc; above it the pure epsilon = 0 schedule is faster
         const char *e = getenv("PM_LAP_SQUARE_SLACK");
         if (e) max_slack = atof(e);
         square = (double)(nc - nr) <= max_slack * (double)nc;
