@@ -501,6 +501,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # (its banner would go to stdout, next to the JSON line)
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = load()
     bid_rounds = args.bid_rounds if args.bid_rounds is not None else 2048

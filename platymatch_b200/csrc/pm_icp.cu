@@ -655,6 +655,11 @@ extern "C" int pm_icp(const double *moving, int n1, const double *fixed, int n2,
         PM_CUDA_TRY(cudaGetDevice(&dev));
         PM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         PM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm_icp_persistent_kernel, PM_ICP_QPB * PM_ICP_LPQ, 0));
+        // Measured on B200 (tools/icp_probe.py, profiles/r2_icp_probe.txt): with up to 2 CTAs per SM the one-launch loop
+        // takes 1.0 ms for 50 iterations at 8k (multi-launch: 2.5 ms); from 3 CTAs per SM on it collapses (335 ms at
+        // 14k, 508 ms at 20k: the CTAs spinning at the grid barrier starve the ones still searching), while the
+        // multi-launch loop stays at 2.6-2.8 ms.  Larger clouds therefore take the multi-launch path.
+        if (per_sm > 2) per_sm = 2;
         if (nb_pers <= sms * per_sm) {
             double *a_out = a_icp;
             void *args[] = {(void *)&moving, (void *)&n1, (void *)&fixed, (void *)&iterations, (void *)&transform, (void *)&grid, (void *)&cell_start,

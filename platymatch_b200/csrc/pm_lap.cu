@@ -1599,18 +1599,32 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
             if (e && atof(e) > 1.0) theta = atof(e);
             e = getenv("PM_LAP_EPS_PHASES");
             if (e && atoi(e) > 0) phases = atoi(e);
+            // The end of an eps phase is a handful of chains that fight sequentially (measured at 8000 x 8000: bulk
+            // kernel 4.0 / 0.8 / 0.4 ms, then 54 / 31 / 14 ms of ONE CTA finishing phases 1-3 to the last row).  The phases
+            // only prepare prices (exactness comes from the finish below), so they are TRUNCATED: the early ones end
+            // when the bulk kernel's parallelism has collapsed, the last `tail_phases` ones also run the tail kernel
+            // (where the dummies bid), which stops carrying displaced rows once `eps_stop` warps are left.
+            int tail_phases = phases, eps_stop = 3, eps_stop_last = 3;   // measured: profiles/r2_lap_eps_truncation.txt
+            e = getenv("PM_LAP_EPS_TAIL_PHASES");
+            if (e && atoi(e) > 0) tail_phases = atoi(e);
+            e = getenv("PM_LAP_EPS_STOP_LIVE");
+            if (e && atoi(e) >= 0) eps_stop = atoi(e);
+            e = getenv("PM_LAP_EPS_STOP_LAST");
+            if (e && atoi(e) >= 0) eps_stop_last = atoi(e);
             const int stop_live = B.stop_live;
-            B.stop_live = 0;                                  // a phase runs to completion
             for (int k = 0; k < phases; ++k, factor /= theta) {
                 B.eps_factor = factor;
+                B.stop_live = (k == phases - 1) ? eps_stop_last : eps_stop;
                 if (k > 0) {
                     pm_ls_phase_reset_kernel<<<dim3(32, batch), 256, 0, s>>>(B);
                     PM_LAUNCH_CHECK();
                 }
                 pm_ls_bulk_kernel<<<batch * bulk_ctas, 256, 0, s>>>(B, bulk_ctas);
                 PM_LAUNCH_CHECK();
-                pm_ls_auction_kernel<<<batch, 1024, tail_smem, s>>>(B);
-                PM_LAUNCH_CHECK();
+                if (k >= phases - tail_phases) {
+                    pm_ls_auction_kernel<<<batch, 1024, tail_smem, s>>>(B);
+                    PM_LAUNCH_CHECK();
+                }
             }
             B.eps_factor = 0.0;
             B.stop_live = stop_live;
