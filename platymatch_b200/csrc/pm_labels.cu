@@ -176,8 +176,14 @@ __device__ __noinline__ void pm_label_chunk(const uint4 q, size_t v0, unsigned p
 #pragma unroll
         for (int e = 0; e < VPC; ++e) ids[e] = (int)((w[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
     }
-    unsigned pz = (unsigned)(v0 / plane);
-    const unsigned rem = (unsigned)(v0 - (size_t)pz * plane);
+    unsigned pz, rem;
+    if (v0 <= 0xFFFFFFFFull) {                    // (almost always: a 32-bit division is ~5x cheaper than a 64-bit one)
+        pz = (unsigned)v0 / plane;
+        rem = (unsigned)v0 - pz * plane;
+    } else {
+        pz = (unsigned)(v0 / plane);
+        rem = (unsigned)(v0 - (size_t)pz * plane);
+    }
     unsigned py = rem / nx, px = rem - py * nx;
     int run_id = 0;
     unsigned k = 0, sx = 0, ry = 0, rz = 0;
@@ -249,42 +255,67 @@ __global__ void __launch_bounds__(256, 4) pm_label_stream_kernel(const T *__rest
     }
 }
 
-// one CTA: ids with a non-zero count, ascending, -> ids / centroids (z, y, x) / sizes
+// one CTA: ids with a non-zero count, ascending, -> ids / centroids (z, y, x) / sizes.
+// Every thread owns a CONTIGUOUS segment of the table (ascending ids stay in order): all its counts are loaded
+// together (one L2 round trip), ONE block scan of the per-thread totals, then the writes.  (The first version walked
+// the table in 1024-entry chunks with four block barriers and a serial scan per chunk: 19 us for 6000 ids.)
+#define PM_LABEL_SEG 8
 __global__ void __launch_bounds__(1024) pm_label_finalize_kernel(const unsigned long long *__restrict__ acc,
                                                                  unsigned table_size, double anisotropy, int capacity,
                                                                  int32_t *__restrict__ ids, double *__restrict__ centroids,
                                                                  double *__restrict__ sizes, int32_t *__restrict__ n_out) {
-    __shared__ int s_scan[33];
+    __shared__ int s_warp[32];
     __shared__ int s_base;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t == 0) s_base = 0;
     __syncthreads();
-    for (unsigned b = 1; b < table_size; b += 1024) {
-        const unsigned id = b + t;
-        const unsigned long long cnt = (id < table_size) ? acc[(size_t)id * 4] : 0ull;
-        const bool has = cnt != 0ull;
-        const unsigned bal = __ballot_sync(0xffffffffu, has);
-        if (lane == 0) s_scan[warp] = __popc(bal);
+    for (unsigned b = 1; b < table_size; b += 1024 * PM_LABEL_SEG) {        // (one trip for up to 8192 ids)
+        const unsigned first = b + (unsigned)t * PM_LABEL_SEG;
+        unsigned long long cnt[PM_LABEL_SEG];
+        int mine = 0;
+#pragma unroll
+        for (int e = 0; e < PM_LABEL_SEG; ++e) {
+            const unsigned id = first + e;
+            cnt[e] = (id < table_size) ? __ldcg(acc + (size_t)id * 4) : 0ull;
+        }
+#pragma unroll
+        for (int e = 0; e < PM_LABEL_SEG; ++e) mine += cnt[e] != 0ull;
+        int incl = mine;                                                    // inclusive scan over the block
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-        if (t == 0) {
-            int a = s_base;
-            for (int w = 0; w < 32; ++w) { const int c = s_scan[w]; s_scan[w] = a; a += c; }
-            s_scan[32] = a;
+        if (warp == 0) {
+            int w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += v;
+            }
+            s_warp[lane] = wi - w;                                          // exclusive offset of every warp
         }
         __syncthreads();
-        if (has) {
-            const int k = s_scan[warp] + __popc(bal & ((1u << lane) - 1u));
-            if (k < capacity) {
-                const double c = (double)cnt;
-                ids[k] = (int32_t)id;
-                centroids[3 * (size_t)k + 0] = (double)acc[(size_t)id * 4 + 1] / c;     // np.mean(z)
-                centroids[3 * (size_t)k + 1] = (double)acc[(size_t)id * 4 + 2] / c;
-                centroids[3 * (size_t)k + 2] = (double)acc[(size_t)id * 4 + 3] / c;
-                sizes[k] = anisotropy * c;                                              // anisotropy * len(z)  (:508)
+        int k = s_base + s_warp[warp] + incl - mine;
+#pragma unroll
+        for (int e = 0; e < PM_LABEL_SEG; ++e) {
+            if (cnt[e] != 0ull) {
+                if (k < capacity) {
+                    const unsigned id = first + e;
+                    const double c = (double)cnt[e];
+                    ids[k] = (int32_t)id;
+                    centroids[3 * (size_t)k + 0] = (double)__ldcg(acc + (size_t)id * 4 + 1) / c;     // np.mean(z)
+                    centroids[3 * (size_t)k + 1] = (double)__ldcg(acc + (size_t)id * 4 + 2) / c;
+                    centroids[3 * (size_t)k + 2] = (double)__ldcg(acc + (size_t)id * 4 + 3) / c;
+                    sizes[k] = anisotropy * c;                                                       // anisotropy * len(z)  (:508)
+                }
+                ++k;
             }
         }
         __syncthreads();
-        if (t == 0) s_base = s_scan[32];
+        if (t == 1023) s_base = k;                                          // (the last thread's k = base + block total)
         __syncthreads();
     }
     if (t == 0) n_out[0] = s_base;

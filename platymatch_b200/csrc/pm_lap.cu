@@ -31,7 +31,7 @@
 namespace cg = cooperative_groups;
 
 // squared (dummy rows + eps-scaling) when nc - nr <= this fraction of nc; measured crossover at 8k, profiles/r2_lap_slack.txt
-#define PM_LAP_SQUARE_SLACK_DEFAULT 0.015
+#define PM_LAP_SQUARE_SLACK_DEFAULT 0.02
 #define PM_LAP_BID_THREADS 1024
 #define PM_LAP_CPT 8
 #define PM_LAP_MAX_THREADS 1024
@@ -124,6 +124,7 @@ struct PmLapBatch {   // passed by value to kernels
     int ring_in_smem;
     // eps-scaling phases (problems without slack columns): increment = certified gap + eps, eps = eps_factor x the
     // matrix' own cost scale (mean candidate-list width, accumulated by pm_ls_build_lists into scale[0..1] per matrix)
+    int dummies_bid;     // tail kernel: dummy rows take part (0 in the early eps phases: they stay free there)
     double eps_factor;   // 0 = exact phase (eps = 0)
     double *scale;       // [batch][2]: sum of list widths, number of rows that contributed
 };
@@ -806,7 +807,7 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
     __syncthreads();
     for (int base = 0; base < nr; base += blockDim.x) {
         const int i = base + t;
-        const bool is_free = (i < nr) && (V.col4row[i] < 0);
+        const bool is_free = (i < nr) && (V.col4row[i] < 0) && (B.dummies_bid || i < B.nr_real);
         const unsigned bal = __ballot_sync(0xffffffffu, is_free);
         if (lane == 0) s_scan[t >> 5] = __popc(bal);
         __syncthreads();
@@ -897,13 +898,27 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
                 // most the cheapest dummy-held column + eps).  The exact phase (eps = 0) bids individually: there the
                 // dummies sit on equal prices (pm_ls_equalise_dummies_kernel) and a displaced one parks at once.
                 w1 = INFINITY; w2 = INFINITY;
+                // two columns per lane and trip (one 16-byte and one 4-byte shared load), four trips in flight
+                const unsigned v_s = (unsigned)__cvta_generic_to_shared(v), o_s = (unsigned)__cvta_generic_to_shared(owner);
 #pragma unroll 4
-                for (int j = lane; j < nc; j += 32) {
-                    const double vj = *reinterpret_cast<volatile double *>(&v[j]), w = -vj;
-                    const unsigned short oj = *reinterpret_cast<volatile unsigned short *>(&owner[j]);
-                    if (eps > 0.0 && oj < PM_LS_LOCKED && (int)oj >= B.nr_real) continue;
-                    if (w < w1) { w2 = w1; w1 = w; bj = j; v1 = vj; }
-                    else if (w < w2) w2 = w;
+                for (int j = 2 * lane; j < nc; j += 64) {
+                    double va, vb;
+                    unsigned oo;
+                    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(va), "=d"(vb) : "r"(v_s + 8u * (unsigned)j));
+                    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(oo) : "r"(o_s + 2u * (unsigned)j));
+                    const unsigned oa = oo & 0xffffu, ob = oo >> 16;
+                    const bool skip_a = eps > 0.0 && oa < PM_LS_LOCKED && (int)oa >= B.nr_real;
+                    const bool skip_b = (j + 1 >= nc) || (eps > 0.0 && ob < PM_LS_LOCKED && (int)ob >= B.nr_real);
+                    if (!skip_a) {
+                        const double w = -va;
+                        if (w < w1) { w2 = w1; w1 = w; bj = j; v1 = va; }
+                        else if (w < w2) w2 = w;
+                    }
+                    if (!skip_b) {
+                        const double w = -vb;
+                        if (w < w1) { w2 = w1; w1 = w; bj = j + 1; v1 = vb; }
+                        else if (w < w2) w2 = w;
+                    }
                 }
             } else {
                 // its 4 list slots at the current prices, branch-free
@@ -1523,6 +1538,7 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
     B.scale = (double *)((char *)workspace + 256);
     B.zero_row = (const float *)((char *)workspace + 256 + pm_lap_align((size_t)batch * 2 * sizeof(double)));
     B.eps_factor = 0.0;
+    B.dummies_bid = 1;
     B.ws = (char *)workspace + pm_lap_header_bytes(batch, B.ncp);
     B.col4row = col4row; B.stats = (long long *)stats; B.total = total;
     // one "round" of the sparse auction = a budget of one bid per row, spread over the 32 warps
@@ -1611,10 +1627,14 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
             if (e && atoi(e) >= 0) eps_stop = atoi(e);
             e = getenv("PM_LAP_EPS_STOP_LAST");
             if (e && atoi(e) >= 0) eps_stop_last = atoi(e);
+            int dummy_phases = phases;                        // the dummies bid in the last `dummy_phases` eps phases
+            e = getenv("PM_LAP_EPS_DUMMY_PHASES");
+            if (e && atoi(e) >= 0) dummy_phases = atoi(e);
             const int stop_live = B.stop_live;
             for (int k = 0; k < phases; ++k, factor /= theta) {
                 B.eps_factor = factor;
                 B.stop_live = (k == phases - 1) ? eps_stop_last : eps_stop;
+                B.dummies_bid = k >= phases - dummy_phases;
                 if (k > 0) {
                     pm_ls_phase_reset_kernel<<<dim3(32, batch), 256, 0, s>>>(B);
                     PM_LAUNCH_CHECK();
@@ -1627,6 +1647,7 @@ extern "C" int pm_lap_solve(const float *cost, int batch, int nr, int nc, int ld
                 }
             }
             B.eps_factor = 0.0;
+            B.dummies_bid = 1;
             B.stop_live = stop_live;
             if (B.nr > B.nr_real) {
                 pm_ls_equalise_dummies_kernel<<<batch, 1024, 0, s>>>(B);
