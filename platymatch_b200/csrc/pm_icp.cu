@@ -445,8 +445,11 @@ pm_icp_persistent_kernel(const double *__restrict__ moving, int n1, const double
         double v[PM_ICP_NSUM];
 #pragma unroll
         for (int q = 0; q < PM_ICP_NSUM; ++q) v[q] = 0.0;
-        // (a whole group of PM_ICP_LPQ lanes is live or not: the shuffles inside stay converged)
-        pm_icp_grid_search<PM_ICP_LPQ>(G, cell_start, sorted_pts, sorted_idx, mx, my, mz, bd, bj);
+        // (a whole group of PM_ICP_LPQ lanes is live or not: the shuffles inside stay converged.  The padding groups of
+        // the last CTA must NOT search: their query (0, 0, 0) lies far outside the cloud and walks the whole grid ring by
+        // ring, ~3.5 ms per iteration while every other CTA waits at the grid barrier - 180-500 ms per call whenever
+        // n1 is not a multiple of 32, found in round 2 with tools/icp_probe.py / tools/square_probe.py)
+        if (live) pm_icp_grid_search<PM_ICP_LPQ>(G, cell_start, sorted_pts, sorted_idx, mx, my, mz, bd, bj);
         if (live) {
             if (bj == 0x7fffffff) bj = 0;        // no finite distance at all: np.argmin of an all-NaN row
             pm_icp_terms(mx, my, mz, shift, fixed, bj, transform, v);
@@ -655,11 +658,6 @@ extern "C" int pm_icp(const double *moving, int n1, const double *fixed, int n2,
         PM_CUDA_TRY(cudaGetDevice(&dev));
         PM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         PM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm_icp_persistent_kernel, PM_ICP_QPB * PM_ICP_LPQ, 0));
-        // Measured on B200 (tools/icp_probe.py, profiles/r2_icp_probe.txt): with up to 2 CTAs per SM the one-launch loop
-        // takes 1.0 ms for 50 iterations at 8k (multi-launch: 2.5 ms); from 3 CTAs per SM on it collapses (335 ms at
-        // 14k, 508 ms at 20k: the CTAs spinning at the grid barrier starve the ones still searching), while the
-        // multi-launch loop stays at 2.6-2.8 ms.  Larger clouds therefore take the multi-launch path.
-        if (per_sm > 2) per_sm = 2;
         if (nb_pers <= sms * per_sm) {
             double *a_out = a_icp;
             void *args[] = {(void *)&moving, (void *)&n1, (void *)&fixed, (void *)&iterations, (void *)&transform, (void *)&grid, (void *)&cell_start,

@@ -150,3 +150,34 @@ def test_config4_20k_assignment_exact_single_gpu(O, torch):
     ro, co = O.linear_sum_assignment(G)
     assert res["lap_cost"][best].item() == pytest.approx(G[ro, co].sum(), rel=1e-12)
     assert np.array_equal(got, co), int((got != co).sum())
+
+
+def test_icp_padding_lanes_do_not_search(O, torch):
+    """Round-2 regression: the one-launch ICP loop pads the last CTA up to 32 moving points; the padding lanes used to
+    run the grid search from (0, 0, 0), far outside the cloud: ~3.5 ms per iteration with the whole grid waiting at the
+    barrier (180-500 ms per call for every n_moving that is not a multiple of 32, i.e. for every real specimen).  Same
+    nearest neighbours as brute force, and the time of a 7801-point cloud stays in the millisecond range."""
+    import os
+    from platymatch_b200 import device as D
+    from platymatch_b200.synthetic import make_pair
+    p = make_pair(8668, seed=4)                       # 7801 moving nuclei = 243 CTAs + 25 of 32 points
+    assert p["moving"].shape[1] % 32 != 0
+    a = p["A_gt"].copy()
+    a[:3, 3] += 2.0
+    m, f = D.to_device_points(p["moving"]), D.to_device_points(p["fixed"])
+    moved = D.apply_affine(m, torch.from_numpy(a.reshape(16)).cuda())
+    D.icp(moved, f, 50)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    a_icp, resid, nn = D.icp(moved, f, 50, want_nn=True)
+    e1.record()
+    torch.cuda.synchronize()
+    assert e0.elapsed_time(e1) < 25.0, e0.elapsed_time(e1)
+    os.environ["PM_ICP_BRUTE"] = "1"
+    try:
+        b_icp, b_resid, b_nn = D.icp(moved, f, 50, want_nn=True)
+    finally:
+        del os.environ["PM_ICP_BRUTE"]
+    assert torch.equal(nn, b_nn)
+    assert float((a_icp - b_icp).abs().max()) < 1e-9
