@@ -487,6 +487,37 @@ def bench_square(torch, args):
             "lap_dijkstra_steps": [int(x[3]) for x in st]}
 
 
+def bench_supervised(torch, args, pair, with_cpu):
+    """BASELINE config 3: keypoint-supervised mode (reference _dock_widget.py:707-717): affine from 10 keypoint pairs,
+    then ICP on the full clouds, through the public numpy API."""
+    import platymatch_b200 as pm
+    from platymatch_b200.synthetic import make_keypoints
+    mk, fk = make_keypoints(pair, 10, seed=0)
+    for _ in range(3):
+        res = pm.estimate_transform_supervised(pair["moving"], pair["fixed"], mk, fk, icp_iterations=ICP_ITERS)
+    reps = 20
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        res = pm.estimate_transform_supervised(pair["moving"], pair["fixed"], mk, fk, icp_iterations=ICP_ITERS)
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    moved = res["transform"] @ np.vstack([pair["moving"], np.ones((1, pair["moving"].shape[1]))])
+    err = float(np.median(np.linalg.norm(moved[:3] - pair["fixed"][:, pair["gt_fixed_index"]], axis=0)))
+    out = {"workload": "%d x %d pair, 10 keypoint pairs (1 px click jitter), affine fit + %d ICP iterations through "
+                       "estimate_transform_supervised(numpy...)" % (pair["moving"].shape[1], pair["fixed"].shape[1], ICP_ITERS),
+           "ms_per_registration": ms, "registrations_per_s": 1e3 / ms, "median_error_px": err,
+           "timing": "host clock around %d calls of the public API with HOST inputs (H2D + D2H inside)" % reps}
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as O
+        O.set_num_threads(len(os.sched_getaffinity(0)))
+        t0 = time.perf_counter()
+        O.estimate_transform_supervised(pair["moving"], pair["fixed"], mk, fk, icp_iterations=ICP_ITERS)
+        out["cpu_baseline"] = {"value": 1.0 / (time.perf_counter() - t0), "unit": "registrations/s", "cores": O.num_threads(),
+                               "kind": "port", "sample": "one complete supervised registration with the oracle port"}
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -720,6 +751,10 @@ def run_b200(args):
     # single-GPU secondary measurements and the CPU baseline (rank 0 at N = 1 only)
     if not args.no_rows and world == 1:
         rows["label_centroids"] = bench_label_row(torch, D, hbm_peak, not args.no_cpu_baseline)
+        try:
+            rows["supervised_8k"] = bench_supervised(torch, args, pairs[0], not args.no_cpu_baseline)
+        except Exception as e:
+            rows["supervised_8k"] = {"error": "%s: %s" % (type(e).__name__, e)}
         if not args.no_square:
             try:
                 rows["square_8k"] = bench_square(torch, args)

@@ -217,17 +217,37 @@ __device__ __noinline__ void pm_label_chunk(const uint4 q, size_t v0, unsigned p
 
 #define PM_LABEL_STREAM_UNROLL 8      // independent 16-byte loads in flight per thread (128 B)
 
-// labels must be 16-byte aligned; the voxels beyond the last full chunk are handled by thread 0 of block 0
+// labels must be 16-byte aligned; the voxels beyond the last full chunk are handled by thread 0 of block 0.
+// Foreground chunks are not processed where they are found: with ~3 % of the chunks touching a nucleus, 5 of the 8
+// chunk slots of a warp trip have SOME lane with foreground, and each of them ran the ~100-instruction run-length
+// path with one or two live lanes (ncu, round 2: 70 warp instructions per 512 bytes, issue slots 62 % busy, 4.6 TB/s).
+// Each warp therefore queues its foreground chunks {16 bytes, chunk index} in shared memory (ballot + popc) and runs
+// the run-length path once 32 are waiting, one chunk per lane.
+#define PM_LABEL_QCAP 64                 // queue slots per warp (a trip adds at most 32 per chunk slot)
 template <typename T>
 __global__ void __launch_bounds__(256, 4) pm_label_stream_kernel(const T *__restrict__ labels, int nz, int ny, int nx,
                                                               unsigned table_size, unsigned long long *__restrict__ acc) {
     constexpr int VPC = 16 / (int)sizeof(T);
+    __shared__ uint4 s_q[8][PM_LABEL_QCAP];
+    __shared__ unsigned s_c[8][PM_LABEL_QCAP];                   // chunk index (the host checks n_chunks < 2^32)
     const size_t n_vox = (size_t)nz * ny * nx;
     const size_t n_chunks = n_vox / VPC;
     const unsigned plane = (unsigned)ny * (unsigned)nx;          // (ny, nx < 2^26 and the host checks ny * nx < 2^32)
     const uint4 *__restrict__ p = reinterpret_cast<const uint4 *>(labels);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += stride * PM_LABEL_STREAM_UNROLL) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    int queued = 0;                                              // warp-uniform
+    auto flush = [&]() {
+        __syncwarp();
+        for (int i = lane; i < queued; i += 32)
+            pm_label_chunk<T>(s_q[w][i], (size_t)s_c[w][i] * VPC, plane, (unsigned)ny, (unsigned)nx, table_size, acc);
+        queued = 0;
+        __syncwarp();
+    };
+    // (the loop bound is the warp's first chunk, so that all 32 lanes stay in the loop for the ballots)
+    for (size_t base = (size_t)blockIdx.x * blockDim.x + (size_t)w * 32; base < n_chunks; base += stride * PM_LABEL_STREAM_UNROLL) {
+        const size_t c = base + lane;
         uint4 q[PM_LABEL_STREAM_UNROLL];
 #pragma unroll
         for (int u = 0; u < PM_LABEL_STREAM_UNROLL; ++u) {
@@ -236,10 +256,22 @@ __global__ void __launch_bounds__(256, 4) pm_label_stream_kernel(const T *__rest
             if (idx < n_chunks) q[u] = __ldcs(p + idx);            // streamed once: evict first
         }
 #pragma unroll
-        for (int u = 0; u < PM_LABEL_STREAM_UNROLL; ++u)
-            if ((q[u].x | q[u].y | q[u].z | q[u].w) != 0u)
-                pm_label_chunk<T>(q[u], (c + (size_t)u * stride) * VPC, plane, (unsigned)ny, (unsigned)nx, table_size, acc);
+        for (int u = 0; u < PM_LABEL_STREAM_UNROLL; ++u) {
+            const bool fg = (q[u].x | q[u].y | q[u].z | q[u].w) != 0u;
+            const unsigned bal = __ballot_sync(0xffffffffu, fg);
+            if (bal) {
+                if (queued + __popc(bal) > PM_LABEL_QCAP) flush();
+                if (fg) {
+                    const int pos = queued + __popc(bal & lt);
+                    s_q[w][pos] = q[u];
+                    s_c[w][pos] = (unsigned)(c + (size_t)u * stride);
+                }
+                queued += __popc(bal);
+            }
+        }
+        if (queued >= 32) flush();
     }
+    flush();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (size_t v = n_chunks * VPC; v < n_vox; ++v) {         // < VPC voxels
             const int id = (int)labels[v];
@@ -255,70 +287,65 @@ __global__ void __launch_bounds__(256, 4) pm_label_stream_kernel(const T *__rest
     }
 }
 
-// one CTA: ids with a non-zero count, ascending, -> ids / centroids (z, y, x) / sizes.
-// Every thread owns a CONTIGUOUS segment of the table (ascending ids stay in order): all its counts are loaded
-// together (one L2 round trip), ONE block scan of the per-thread totals, then the writes.  (The first version walked
-// the table in 1024-entry chunks with four block barriers and a serial scan per chunk: 19 us for 6000 ids.)
-#define PM_LABEL_SEG 8
+// ids with a non-zero count, ascending (np.unique order), -> ids / centroids (z, y, x) / sizes.
+// One CTA per 1024 ids, one id per thread: the three float64 divisions per nucleus and the loads of its sums spread
+// over as many SMs as there are chunks (one CTA doing all of it took 19-36 us for 6000 ids, a quarter of the whole
+// label pass).  The output offset of a chunk = the number of non-empty ids before it, which every CTA counts itself
+// from the table (b x 1024 count loads for chunk b, all in flight together: no second launch, no inter-CTA
+// dependency; quadratic only in the number of chunks, ~1 ms for a million ids).
 __global__ void __launch_bounds__(1024) pm_label_finalize_kernel(const unsigned long long *__restrict__ acc,
                                                                  unsigned table_size, double anisotropy, int capacity,
                                                                  int32_t *__restrict__ ids, double *__restrict__ centroids,
                                                                  double *__restrict__ sizes, int32_t *__restrict__ n_out) {
     __shared__ int s_warp[32];
-    __shared__ int s_base;
+    __shared__ int s_before;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (t == 0) s_base = 0;
+    const unsigned first = 1u + blockIdx.x * 1024u;                 // ids of this chunk: first .. first + 1023
+    const unsigned id = first + (unsigned)t;
+    const unsigned long long cnt = (id < table_size) ? __ldcg(acc + (size_t)id * 4) : 0ull;
+    unsigned long long sz = 0ull, sy = 0ull, sx = 0ull;
+    if (cnt) {                                                      // (issued before the counting loop: in flight with it)
+        sz = __ldcg(acc + (size_t)id * 4 + 1); sy = __ldcg(acc + (size_t)id * 4 + 2); sx = __ldcg(acc + (size_t)id * 4 + 3);
+    }
+    int before = 0;                                                 // non-empty ids in the chunks before this one
+#pragma unroll 4
+    for (unsigned j = 1u + (unsigned)t; j < first; j += 1024u) before += __ldcg(acc + (size_t)j * 4) != 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    const unsigned bal = __ballot_sync(0xffffffffu, cnt != 0ull);
+    if (lane == 0) s_warp[warp] = before;                           // (reused below for the in-chunk scan)
     __syncthreads();
-    for (unsigned b = 1; b < table_size; b += 1024 * PM_LABEL_SEG) {        // (one trip for up to 8192 ids)
-        const unsigned first = b + (unsigned)t * PM_LABEL_SEG;
-        unsigned long long cnt[PM_LABEL_SEG];
-        int mine = 0;
-#pragma unroll
-        for (int e = 0; e < PM_LABEL_SEG; ++e) {
-            const unsigned id = first + e;
-            cnt[e] = (id < table_size) ? __ldcg(acc + (size_t)id * 4) : 0ull;
-        }
-#pragma unroll
-        for (int e = 0; e < PM_LABEL_SEG; ++e) mine += cnt[e] != 0ull;
-        int incl = mine;                                                    // inclusive scan over the block
+    if (t == 0) {
+        int a = 0;
+        for (int w = 0; w < 32; ++w) a += s_warp[w];
+        s_before = a;
+    }
+    __syncthreads();
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+        const int w = s_warp[lane];
+        int wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
+            const int v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
         }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int w = s_warp[lane], wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += v;
-            }
-            s_warp[lane] = wi - w;                                          // exclusive offset of every warp
-        }
-        __syncthreads();
-        int k = s_base + s_warp[warp] + incl - mine;
-#pragma unroll
-        for (int e = 0; e < PM_LABEL_SEG; ++e) {
-            if (cnt[e] != 0ull) {
-                if (k < capacity) {
-                    const unsigned id = first + e;
-                    const double c = (double)cnt[e];
-                    ids[k] = (int32_t)id;
-                    centroids[3 * (size_t)k + 0] = (double)__ldcg(acc + (size_t)id * 4 + 1) / c;     // np.mean(z)
-                    centroids[3 * (size_t)k + 1] = (double)__ldcg(acc + (size_t)id * 4 + 2) / c;
-                    centroids[3 * (size_t)k + 2] = (double)__ldcg(acc + (size_t)id * 4 + 3) / c;
-                    sizes[k] = anisotropy * c;                                                       // anisotropy * len(z)  (:508)
-                }
-                ++k;
-            }
-        }
-        __syncthreads();
-        if (t == 1023) s_base = k;                                          // (the last thread's k = base + block total)
-        __syncthreads();
+        s_warp[lane] = wi - w;                                      // exclusive offset of every warp
+        if (lane == 31 && blockIdx.x == gridDim.x - 1) n_out[0] = s_before + wi;
     }
-    if (t == 0) n_out[0] = s_base;
+    __syncthreads();
+    if (cnt) {
+        const int k = s_before + s_warp[warp] + __popc(bal & ((1u << lane) - 1u));
+        if (k < capacity) {
+            const double c = (double)cnt;
+            ids[k] = (int32_t)id;
+            centroids[3 * (size_t)k + 0] = (double)sz / c;                                   // np.mean(z)
+            centroids[3 * (size_t)k + 1] = (double)sy / c;
+            centroids[3 * (size_t)k + 2] = (double)sx / c;
+            sizes[k] = anisotropy * c;                                                       // anisotropy * len(z)  (:508)
+        }
+    }
 }
 
 template <typename T>
@@ -333,7 +360,7 @@ static int pm_label_run(const T *labels, int nz, int ny, int nx, unsigned table_
     size_t want = (n_vox + 1023) / 1024;
     const int blocks = (int)(want < (size_t)sms * 8 ? (want ? want : 1) : (size_t)sms * 8);   // 8 resident CTAs per SM
     const bool stream_ok = (reinterpret_cast<size_t>(labels) & 15) == 0 && (size_t)ny * nx < ((size_t)1 << 32) &&
-                           !getenv("PM_LABEL_WARP_KERNEL");
+                           n_vox / (16 / sizeof(T)) < ((size_t)1 << 32) && !getenv("PM_LABEL_WARP_KERNEL");
     if (stream_ok) {
         // 128 B per thread in flight; a grid of whole waves (8 CTAs of 256 threads per SM)
         const size_t chunks = n_vox / (16 / sizeof(T));
@@ -344,7 +371,8 @@ static int pm_label_run(const T *labels, int nz, int ny, int nx, unsigned table_
         pm_label_accumulate_kernel<T><<<blocks, 256, 0, s>>>(labels, nz, ny, nx, table_size, acc);
     }
     PM_LAUNCH_CHECK();
-    pm_label_finalize_kernel<<<1, 1024, 0, s>>>(acc, table_size, anisotropy, capacity, ids, centroids, sizes, n_out);
+    const unsigned chunks = table_size > 1 ? (table_size - 1 + 1023) / 1024 : 1;
+    pm_label_finalize_kernel<<<chunks, 1024, 0, s>>>(acc, table_size, anisotropy, capacity, ids, centroids, sizes, n_out);
     PM_LAUNCH_CHECK();
     return PM_OK;
 }
