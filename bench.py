@@ -35,7 +35,8 @@ TRIALS = 8000
 ICP_ITERS = 50
 FLOP_PER_PAIR = 1801.0        # 5 FLOP per bin pair x 360 + 1
 METRIC = "registrations/sec"
-CHI2_NCU_DRAM_BYTES = 186.0e6     # measured once with ncu at the headline size (10.6 MB read + 175.4 MB written)
+CHI2_NCU_DRAM_BYTES = 186.9e6     # ncu --set full at the headline size, round 2 (10.7 MB read + 176.2 MB written)
+CHI2_NCU_DRAM_BYTES_DENSE = 196.2e6   # the filled-ellipsoid pair (20.2 MB read + 176.0 MB written), profiles/r2_chi2_kernel_dense.txt
 
 
 def workload_config(n1, n2, trials):
@@ -657,9 +658,10 @@ def run_b200(args):
                          "shell cloud (the headline workload)")
     roof["traffic"] = CHI2_NCU_DRAM_BYTES if (n1, n2) == (7200, 8000) else None
     roof["traffic_source"] = ("ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
-                              "(profiles/r1_chi2_kernel.txt)")
+                              "(profiles/r2_chi2_kernel_shell.txt: 10.7 MB read + 176.2 MB written; the tail of the matrix is still in L2)")
     roof["dense"] = chi2_roofline(torch, D, P, make_pair(args.n_fixed, filled=True), bufs, fp32_probe, fp32_nominal, hbm_peak,
                                   "filled ellipsoid (late-stage embryo, SURVEY §8d): ~2x more bins populated per histogram")
+    roof["dense"]["traffic"] = CHI2_NCU_DRAM_BYTES_DENSE if (n1, n2) == (7200, 8000) else None
     chi2_gpairs = roof["gpairs_per_s"]
 
     # ---- secondary: independent registrations overlapped on separate streams (one host thread each) ----
