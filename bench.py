@@ -240,7 +240,8 @@ def bench_label_row(torch, D, hbm_peak, with_cpu):
     ms = 0.0
     for _ in range(reps):
         flush.fill_(1)
-        e0.record()
+        flush.fill_(2)              # (twice: ~100 us of device work, so that the host is ahead when the timed region starts
+        e0.record()                 #  and the region measures the device pass, not Python's launch latency)
         D.label_centroids(dev, 1.0, table_size=n_nuclei + 1, sync=False)          # memset + accumulate + compact
         e1.record()
         torch.cuda.synchronize()
@@ -250,7 +251,7 @@ def bench_label_row(torch, D, hbm_peak, with_cpu):
            "ms": ms, "voxels_per_s": vol.size / (ms * 1e-3),
            "roofline": {"kernel": "pm_label_stream_kernel (+ memset of the table + pm_label_finalize_kernel inside the timed region)", "bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9,
                         "peak": hbm_peak, "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak, "of": "measured",
-                        "algorithmic_bytes": nbytes, "l2": "160 MB flush between repetitions"}}
+                        "algorithmic_bytes": nbytes, "l2": "160 MB flush (x2) between repetitions"}}
     if with_cpu:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle as O

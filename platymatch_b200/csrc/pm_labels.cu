@@ -216,6 +216,7 @@ __device__ __noinline__ void pm_label_chunk(const uint4 q, size_t v0, unsigned p
 }
 
 #define PM_LABEL_STREAM_UNROLL 8      // independent 16-byte loads in flight per thread (128 B)
+#define PM_LABEL_STREAM_HALF 4        // ... in two register buffers of 4 (software pipeline)
 
 // labels must be 16-byte aligned; the voxels beyond the last full chunk are handled by thread 0 of block 0.
 // Foreground chunks are not processed where they are found: with ~3 % of the chunks touching a nucleus, 5 of the 8
@@ -225,7 +226,7 @@ __device__ __noinline__ void pm_label_chunk(const uint4 q, size_t v0, unsigned p
 // the run-length path once 32 are waiting, one chunk per lane.
 #define PM_LABEL_QCAP 64                 // queue slots per warp (a trip adds at most 32 per chunk slot)
 template <typename T>
-__global__ void __launch_bounds__(256, 4) pm_label_stream_kernel(const T *__restrict__ labels, int nz, int ny, int nx,
+__global__ void __launch_bounds__(256, 3) pm_label_stream_kernel(const T *__restrict__ labels, int nz, int ny, int nx,
                                                               unsigned table_size, unsigned long long *__restrict__ acc) {
     constexpr int VPC = 16 / (int)sizeof(T);
     __shared__ uint4 s_q[8][PM_LABEL_QCAP];
@@ -246,17 +247,21 @@ __global__ void __launch_bounds__(256, 4) pm_label_stream_kernel(const T *__rest
         __syncwarp();
     };
     // (the loop bound is the warp's first chunk, so that all 32 lanes stay in the loop for the ballots)
-    for (size_t base = (size_t)blockIdx.x * blockDim.x + (size_t)w * 32; base < n_chunks; base += stride * PM_LABEL_STREAM_UNROLL) {
-        const size_t c = base + lane;
-        uint4 q[PM_LABEL_STREAM_UNROLL];
+    // Software pipeline: two register buffers of PM_LABEL_STREAM_HALF chunks; the loads of the next half-trip are
+    // issued BEFORE the current one is examined, so a warp always has loads in flight (the first version loaded 8,
+    // examined 8, loaded 8 ...: nothing in flight while it worked).
+    const size_t step = stride * PM_LABEL_STREAM_HALF;
+    auto load = [&](uint4 (&q)[PM_LABEL_STREAM_HALF], size_t base) {
 #pragma unroll
-        for (int u = 0; u < PM_LABEL_STREAM_UNROLL; ++u) {
-            const size_t idx = c + (size_t)u * stride;
+        for (int u = 0; u < PM_LABEL_STREAM_HALF; ++u) {
+            const size_t idx = base + lane + (size_t)u * stride;
             q[u] = make_uint4(0u, 0u, 0u, 0u);
             if (idx < n_chunks) q[u] = __ldcs(p + idx);            // streamed once: evict first
         }
+    };
+    auto examine = [&](const uint4 (&q)[PM_LABEL_STREAM_HALF], size_t base) {
 #pragma unroll
-        for (int u = 0; u < PM_LABEL_STREAM_UNROLL; ++u) {
+        for (int u = 0; u < PM_LABEL_STREAM_HALF; ++u) {
             const bool fg = (q[u].x | q[u].y | q[u].z | q[u].w) != 0u;
             const unsigned bal = __ballot_sync(0xffffffffu, fg);
             if (bal) {
@@ -264,12 +269,25 @@ __global__ void __launch_bounds__(256, 4) pm_label_stream_kernel(const T *__rest
                 if (fg) {
                     const int pos = queued + __popc(bal & lt);
                     s_q[w][pos] = q[u];
-                    s_c[w][pos] = (unsigned)(c + (size_t)u * stride);
+                    s_c[w][pos] = (unsigned)(base + lane + (size_t)u * stride);
                 }
                 queued += __popc(bal);
             }
         }
         if (queued >= 32) flush();
+    };
+    uint4 qa[PM_LABEL_STREAM_HALF], qb[PM_LABEL_STREAM_HALF];
+    size_t base = (size_t)blockIdx.x * blockDim.x + (size_t)w * 32;
+    if (base < n_chunks) load(qa, base);
+    while (base < n_chunks) {
+        const size_t next = base + step;                         // (warp-uniform)
+        if (next < n_chunks) load(qb, next);
+        examine(qa, base);
+        if (!(next < n_chunks)) break;
+        const size_t next2 = next + step;
+        if (next2 < n_chunks) load(qa, next2);
+        examine(qb, next);
+        base = next2;
     }
     flush();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -362,10 +380,17 @@ static int pm_label_run(const T *labels, int nz, int ny, int nx, unsigned table_
     const bool stream_ok = (reinterpret_cast<size_t>(labels) & 15) == 0 && (size_t)ny * nx < ((size_t)1 << 32) &&
                            n_vox / (16 / sizeof(T)) < ((size_t)1 << 32) && !getenv("PM_LABEL_WARP_KERNEL");
     if (stream_ok) {
-        // 128 B per thread in flight; a grid of whole waves (8 CTAs of 256 threads per SM)
+        // ONE wave of resident CTAs (the kernel is a grid-stride loop): no second wave that starts ragged
         const size_t chunks = n_vox / (16 / sizeof(T));
-        size_t want2 = (chunks + 256 * PM_LABEL_STREAM_UNROLL - 1) / (256 * PM_LABEL_STREAM_UNROLL);
-        const int blocks2 = (int)(want2 < (size_t)sms * 8 ? (want2 ? want2 : 1) : (size_t)sms * 8);
+        static int occ_cache[64];                                  // per device (benign race: every writer stores the same value)
+        int occ = (dev >= 0 && dev < 64) ? occ_cache[dev] : 0;
+        if (occ < 1) {
+            PM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pm_label_stream_kernel<T>, 256, 0));
+            if (occ < 1) occ = 1;
+            if (dev >= 0 && dev < 64) occ_cache[dev] = occ;
+        }
+        size_t want2 = (chunks + 256 * PM_LABEL_STREAM_HALF - 1) / (256 * PM_LABEL_STREAM_HALF);
+        const int blocks2 = (int)(want2 < (size_t)sms * occ ? (want2 ? want2 : 1) : (size_t)sms * occ);
         pm_label_stream_kernel<T><<<blocks2, 256, 0, s>>>(labels, nz, ny, nx, table_size, acc);
     } else {
         pm_label_accumulate_kernel<T><<<blocks, 256, 0, s>>>(labels, nz, ny, nx, table_size, acc);

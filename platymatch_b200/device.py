@@ -276,7 +276,7 @@ def label_centroids(labels, anisotropy=1.0, table_size=None, sync=True):
     ids = torch.empty(cap, dtype=torch.int32, device=dev)
     cen = torch.empty((cap, 3), dtype=torch.float64, device=dev)
     sizes = torch.empty(cap, dtype=torch.float64, device=dev)
-    n_out = torch.zeros(1, dtype=torch.int32, device=dev)
+    n_out = torch.empty(1, dtype=torch.int32, device=dev)            # (always written by the finalize kernel)
     nbytes = load().pm_label_workspace_bytes(table_size)
     ws = torch.empty(nbytes // 8 + 1, dtype=torch.int64, device=dev)
     check(load().pm_label_centroids(ptr(labels), dtype, nz, ny, nx, table_size, float(anisotropy), cap, ptr(ids), ptr(cen),
