@@ -35,6 +35,7 @@ TRIALS = 8000
 ICP_ITERS = 50
 FLOP_PER_PAIR = 1801.0        # 5 FLOP per bin pair x 360 + 1
 METRIC = "registrations/sec"
+ALLPAIRS_IN_FLIGHT = 8            # measured on one GPU (tools/allpairs_bench.py): 19.5 / 39 / 50 / 65 / 72 pairs/s with 1 / 3 / 4 / 6 / 8
 CHI2_NCU_DRAM_BYTES = 186.9e6     # ncu --set full at the headline size, round 2 (10.7 MB read + 176.2 MB written)
 CHI2_NCU_DRAM_BYTES_DENSE = 196.2e6   # the filled-ellipsoid pair (20.2 MB read + 176.0 MB written), profiles/r2_chi2_kernel_dense.txt
 
@@ -58,7 +59,7 @@ def parse():
     ap.add_argument("--bid-rounds", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stages", action="store_true", help="print a per-stage device-time breakdown to stderr")
-    ap.add_argument("--in-flight", type=int, default=3,
+    ap.add_argument("--in-flight", type=int, default=6,
                     help="registrations in flight per GPU for the secondary `pipelined` throughput number (0 = skip)")
     ap.add_argument("--no-rows", action="store_true", help="skip the secondary measurements of the widened rows")
     ap.add_argument("--no-square", action="store_true", help="skip the equal-counts (no slack columns) registration row")
@@ -429,7 +430,7 @@ def bench_allpairs(torch, dist, world, rank, args, vary=0.05, runs=2):
     specs = make_specimens(12, n, seed=0, vary=vary)
     clouds = [sp["points"] for sp in specs]
     kw = dict(ransac_trials=args.trials, icp_iterations=ICP_ITERS)
-    PD.register_all_pairs(clouds[:4], in_flight=3, **kw)                # warm-up (6 pairs)
+    PD.register_all_pairs(clouds[:4], in_flight=ALLPAIRS_IN_FLIGHT, **kw)                # warm-up (6 pairs)
     best, st_best = None, None
     for _ in range(runs):
         st = {}
@@ -437,7 +438,7 @@ def bench_allpairs(torch, dist, world, rank, args, vary=0.05, runs=2):
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        pairs, T = PD.register_all_pairs(clouds, in_flight=3, stats=st, **kw)
+        pairs, T = PD.register_all_pairs(clouds, in_flight=ALLPAIRS_IN_FLIGHT, stats=st, **kw)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -457,8 +458,9 @@ def bench_allpairs(torch, dist, world, rank, args, vary=0.05, runs=2):
         gt = specs[j]["A"] @ np.linalg.inv(specs[i]["A"])
         pts = np.vstack([specs[i]["points"][:, :500], np.ones((1, 500))])
         ok += bool(np.median(np.linalg.norm((tr @ pts)[:3] - (gt @ pts)[:3], axis=0)) < 4.0)
-    return {"workload": "12 specimens (%s nuclei), %d pairs, %d GPU(s), 3 registrations in flight per GPU, shared work counter"
-                        % ("%d-%d" % (min(c.shape[1] for c in clouds), max(c.shape[1] for c in clouds)), len(pairs), world),
+    return {"workload": "12 specimens (%s nuclei), %d pairs, %d GPU(s), %d registrations in flight per GPU, shared work counter"
+                        % ("%d-%d" % (min(c.shape[1] for c in clouds), max(c.shape[1] for c in clouds)), len(pairs), world,
+                           ALLPAIRS_IN_FLIGHT),
             "seconds": dt, "pairs_per_s": len(pairs) / dt, "recovered": int(ok), "pairs": len(pairs),
             "timing": "host clock around register_all_pairs with HOST inputs (descriptors of the 12 specimens, H2D and the "
                       "result gather inside), barrier + synchronize on both sides, max over ranks, best of %d" % runs,
@@ -689,16 +691,17 @@ def run_b200(args):
 
         run_all(2 * nfl)                                   # warm-up
         barrier()
+        psteps = max(args.steps, 4 * nfl)                  # (every stream gets at least 4 registrations)
         t0 = time.perf_counter()
-        run_all(args.steps)
+        run_all(psteps)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
             tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
-        pipelined = {"value": world * args.steps / dt, "unit": "registrations/s", "in_flight_per_gpu": nfl,
-                     "ms_per_registration": dt / args.steps * 1e3,
+        pipelined = {"value": world * psteps / dt, "unit": "registrations/s", "in_flight_per_gpu": nfl,
+                     "registrations_per_gpu": psteps, "ms_per_registration": dt / psteps * 1e3,
                      "note": "independent registrations overlapped on %d CUDA streams per GPU (host clock, inputs "
                              "resident); the headline `value` registers one pair at a time" % nfl}
         del bufs

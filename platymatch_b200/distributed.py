@@ -27,6 +27,7 @@ library and are covered by tests/test_gpu_distributed.py (torchrun, NCCL, 2 GPUs
 """
 import itertools
 import os
+import collections
 import threading
 import time
 
@@ -423,7 +424,7 @@ def describe_specimens(specimens, n_variants=4, group=None):
     return out
 
 
-def register_all_pairs(specimens, *, group=None, in_flight=3, dynamic=True, stats=None, **kw):
+def register_all_pairs(specimens, *, group=None, in_flight=6, dynamic=True, stats=None, **kw):
     """Batched all-pairs registration (config 5): descriptors of each specimen are computed once (spread over the
     ranks, all-gathered), the pairs are pulled from one shared work counter by every in-flight worker of every rank
     (`dynamic=False`: static round-robin), the 4x4 results are gathered on every rank.
@@ -452,14 +453,23 @@ def register_all_pairs(specimens, *, group=None, in_flight=3, dynamic=True, stat
             torch.cuda.set_device(dev)
             with torch.cuda.stream(torch.cuda.Stream()):
                 mine = iter(static[w::nfl])
-                results = []
+                results, queued = [], collections.deque()
                 while True:
+                    # A registration is ENQUEUED in ~0.5 ms and runs for 20-100 ms: a worker that pulled as fast as it can
+                    # enqueue would claim the whole counter before its first pair has finished (measured at 4 GPUs: 21 /
+                    # 18 / 22 / 5 pairs per rank).  At most two registrations of a worker are unfinished at any time
+                    # (one running, one queued behind it), so the counter follows the progress of the GPUs.
+                    if len(queued) >= 2:
+                        queued.popleft().synchronize()
                     k = counter.next() if dynamic else next(mine, len(pairs))
                     if k >= len(pairs):
                         break
                     i, j = pairs[k]     # moving = specimen i, fixed = specimen j (tall problems are transposed inside)
                     res = P.register_described(desc[i], desc[j], seed=k, overlap_hypotheses=(nfl == 1), **kw)
                     results.append((k, res["transform"]))
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    queued.append(ev)
                 torch.cuda.current_stream().synchronize()
                 for k, t in results:
                     local[k] = t.cpu().numpy().reshape(4, 4)
