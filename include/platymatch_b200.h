@@ -146,6 +146,11 @@ int pm_chi2_cost(const float *a_t, int lda, const uint32_t *a_mask, int n1, cons
  * (the host mirror transposes otherwise, as scipy does).  Exact, two phases: an epsilon = 0 auction
  * (keeps complementary slackness exactly) followed by shortest augmenting paths with float64 duals
  * for the rows the auction parks — optimal for the float32 matrix given.
+ * Problems with few or no slack columns (nc - nr <= 2 % of nc: specimens of equal size) are solved as
+ * a square problem with nc - nr zero-cost dummy rows: truncated eps-scaling phases of the same auction
+ * prepare the prices, then an exact finish (tight filter, epsilon = 0 auction, augmenting paths)
+ * restores exact complementary slackness: same optimum, same call.  The statistics then count the
+ * dummy rows as well (rows_after_bidding, augmentations).
  *   algorithm  PM_LAP_ALGO_AUTO picks the sparse asynchronous auction (certified candidate lists,
  *              prices in shared memory) whenever the column prices fit in shared memory, else the
  *              dense grid-wide auction; max_bid_rounds = 0 skips the auction (pure augmenting paths);
