@@ -856,8 +856,9 @@ __global__ void __launch_bounds__(1024, 1) pm_ls_auction_kernel(PmLapBatch B) {
         // A DUMMY row (row >= nr_real: all costs zero, present when a problem with few slack columns was made square) has
         // no use for a candidate list: its reduced values are just the negated prices, so it bids from one sweep over the
         // prices (exact best / second best, no certificate needed).  All dummies want the same column, the most expensive
-        // one: bidding for them concurrently means that every commit invalidates the sweeps of all the others (measured:
-        // ~2 ms per dummy and solve at 8k).  ONE warp at a time bids for a dummy; the others put theirs back in the queue.
+        // one: bidding for them concurrently means that every commit invalidates the sweeps of all the others.  ONE warp
+        // at a time bids for a dummy; the others put theirs back in the queue.  (The large cost of the dummies, 2.3 ms each
+        // per solve, was the chain of individual bids, see the class rule below; the token alone did not change it.)
         const bool dummy = row >= B.nr_real;
         if (dummy) {
             int got = 0;
