@@ -78,8 +78,9 @@ def test_detections_from_labels_bit_exact(shape, n, dtype, sparse):
 
 @pytest.mark.gpu
 def test_label_kernels_agree(monkeypatch):
-    """The round-2 streaming kernel (per-thread run-length items) and the round-1 warp-cooperative kernel (kept for
-    unaligned volumes, PM_LABEL_WARP_KERNEL=1) produce identical tables on a crowded volume with touching nuclei."""
+    """The round-2 streaming kernel (per-thread run-length items), the round-1 warp-cooperative kernel (kept for
+    unaligned volumes, PM_LABEL_WARP_KERNEL=1) and the bulk-copy staged variant (PM_LABEL_TMA=1) produce identical
+    tables on a crowded volume with touching nuclei."""
     from platymatch_b200.synthetic import make_label_volume
     from platymatch_b200.utils.labels import detections_from_labels
     for shape, dtype in (((70, 83, 101), np.int32), ((70, 83, 101), np.uint16), ((16, 16, 1030), np.int32)):
@@ -88,8 +89,11 @@ def test_label_kernels_agree(monkeypatch):
         monkeypatch.setenv("PM_LABEL_WARP_KERNEL", "1")
         b = detections_from_labels(vol)
         monkeypatch.delenv("PM_LABEL_WARP_KERNEL")
-        for x, y in zip(a, b):
-            assert np.array_equal(x, y)
+        monkeypatch.setenv("PM_LABEL_TMA", "1")              # the bulk-copy (cp.async.bulk + mbarrier) staged variant
+        c = detections_from_labels(vol)
+        monkeypatch.delenv("PM_LABEL_TMA")
+        for x, y, z in zip(a, b, c):
+            assert np.array_equal(x, y) and np.array_equal(x, z)
 
 
 @pytest.mark.gpu
